@@ -1,0 +1,147 @@
+/*
+ * modelx_digest.h -- C ABI of libmodelxdigest.so, the B200-native digest-and-chunk engine that
+ * replaces the CPU hot path of kubegems/modelx push/pull.
+ *
+ * The reference (Go, CGO_ENABLED=0) has no FFI; the seams this ABI replaces are plain Go calls.
+ * Each entry point below cites the reference call site (file:line under the modelx tree) whose
+ * work it takes over.  INTEGRATION.md shows the cgo binding a maintainer would add.
+ *
+ * Conventions
+ *   - Every function is thread-safe and re-entrant (the reference calls the path from up to 3
+ *     goroutines per Push/Pull, pkg/client/push.go:27, progress/mbar.go:47-51).
+ *   - Return value: MXD_OK (0) or a negative mxd_status.  The caller owns every buffer; the
+ *     library keeps no pointer after a call returns (except the mxd_dev_* enqueue calls, which
+ *     are asynchronous on the given CUDA stream, as documented there).
+ *   - Digests are raw 32-byte SHA-256 values; mxd_digest_string() renders the reference's
+ *     "sha256:<64 hex>" form (go-digest v1.0.0 Digest.String()).
+ *   - There is NO CPU fallback: without a usable CUDA device mxd_open fails with
+ *     MXD_ERR_NO_DEVICE and nothing else can be called.
+ *   - Plain C types only: pointers, sizes, integers.  Device pointers are raw CUDA device
+ *     addresses (e.g. torch.Tensor.data_ptr()), streams are cudaStream_t passed as void*.
+ */
+#ifndef MODELX_DIGEST_H
+#define MODELX_DIGEST_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MXD_ABI_VERSION 1
+
+typedef enum mxd_status {
+    MXD_OK = 0,
+    MXD_ERR_INVALID = -1,      /* bad argument (reference: would be a Go panic or DIGEST_INVALID, pkg/errors/errors.go:69) */
+    MXD_ERR_NO_DEVICE = -2,    /* no CUDA device / driver: the engine refuses to run on the CPU */
+    MXD_ERR_CUDA = -3,         /* a CUDA call failed; mxd_last_error() has the text (maps to INTERNAL, errors.go:65) */
+    MXD_ERR_IO = -4,           /* open/read failed; errno preserved (reference returns the os error) */
+    MXD_ERR_NOMEM = -5,
+    MXD_ERR_CANCELED = -6,     /* mxd_cancel() was called (reference: ctx cancel closes the fd, push.go:156-159) */
+    MXD_ERR_DIV_ZERO = -7      /* calcParts with 0 parts: the reference panics (extension_s3.go:100) */
+} mxd_status;
+
+typedef struct mxd_ctx mxd_ctx;
+typedef struct mxd_hasher mxd_hasher;
+typedef struct { const void* ptr; uint64_t len; } mxd_span;   /* host or device memory */
+typedef struct { int64_t offset, length; } mxd_part;          /* PartRange{offset,length}, extension_s3.go:91-97 */
+
+typedef struct {
+    uint64_t kernel_launches;   /* SHA-256 / compare / generator kernels launched by this context */
+    uint64_t bytes_hashed;      /* message bytes submitted to the SHA-256 kernel */
+    uint64_t h2d_bytes, d2h_bytes;
+    uint64_t reserved[4];
+} mxd_stats;
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+/* devices/ndev: CUDA ordinals to drive from this process (ndev == 0: all visible devices).
+ * ring_bytes: pinned host ring + device ring per device for streaming host data (0 = default). */
+int  mxd_open(mxd_ctx** out, const int* devices, int ndev, uint64_t ring_bytes);
+void mxd_close(mxd_ctx* ctx);
+int  mxd_device_count(const mxd_ctx* ctx);
+void mxd_cancel(mxd_ctx* ctx);              /* abort in-flight streaming calls with MXD_ERR_CANCELED */
+void mxd_reset_cancel(mxd_ctx* ctx);
+int  mxd_get_stats(const mxd_ctx* ctx, mxd_stats* out);
+const char* mxd_strerror(int status);
+const char* mxd_last_error(void);           /* thread-local detail of the last failure on this thread */
+int  mxd_abi_version(void);
+
+/* ---- whole-message digests: the reference's semantics ------------------------------------
+ * digest.FromBytes / digest.FromReader: one SHA-256 over the whole byte string.
+ * One message is one serial chain, so a single call runs on a single GPU lane; throughput
+ * comes from batching many messages (mxd_sha256_batch / mxd_sha256_files). */
+int mxd_sha256(mxd_ctx*, const void* data, uint64_t n, uint8_t out[32]);                 /* digest.Canonical.FromBytes, push.go:25 */
+int mxd_sha256_batch(mxd_ctx*, const mxd_span* spans, uint64_t n, uint8_t* out /*n*32*/);  /* n x FromBytes, host or device spans */
+int mxd_sha256_file(mxd_ctx*, const char* path, uint8_t out[32], uint64_t* size);        /* Client.digest, push.go:149-161; pull.go:116 */
+int mxd_sha256_files(mxd_ctx*, const char* const* paths, uint64_t n, uint8_t* out /*n*32*/,
+                     uint64_t* sizes /*n, may be NULL*/);                                /* Push/PullBlobs fan-out, push.go:36-52, pull.go:41-50 */
+/* pull.go:115-123: "do I already have this blob?"  ok[i] = 1 iff SHA-256(span i) == want[i]. */
+int mxd_verify_batch(mxd_ctx*, const mxd_span* spans, const uint8_t* want /*n*32*/, uint64_t n, uint8_t* ok /*n*/);
+int mxd_verify_files(mxd_ctx*, const char* const* paths, const uint8_t* want /*n*32*/, uint64_t n, uint8_t* ok /*n*/);
+
+/* ---- incremental hasher: hash.Hash shape for TGZ's io.MultiWriter (helper.go:46-49) --------
+ * write never fails for lack of data; sum does not disturb the state (Go: Sum appends a copy). */
+int  mxd_hasher_new(mxd_ctx*, mxd_hasher** out);
+int  mxd_hasher_write(mxd_hasher*, const void* data, uint64_t n);
+int  mxd_hasher_sum(mxd_hasher*, uint8_t out[32]);
+int  mxd_hasher_reset(mxd_hasher*);
+uint64_t mxd_hasher_size(const mxd_hasher*);   /* bytes written so far */
+void mxd_hasher_free(mxd_hasher*);
+
+/* ---- chunked tree digest (new; what lets one blob use every lane and every GPU) -----------
+ * "modelx.tree.v1": leaf i = SHA-256 of bytes [i*leaf, (i+1)*leaf); every following level hashes
+ * groups of `fanout = chunk/leaf` consecutive digests; level 1 are the chunk digests (one per
+ * `chunk` bytes, the list a manifest carries); levels repeat until one digest (top) is left;
+ * root = SHA-256("modelx.tree.v1\0\0" || LE64(size) || LE64(leaf) || LE32(fanout) || LE32(0) || top).
+ * Every node is a plain SHA-256 of well-defined bytes (bit-exact vs crypto/sha256 on them).
+ * The root is NOT the reference's whole-file digest; see DESIGN.md.
+ * chunk must be a multiple of leaf, leaf a multiple of 64, chunk/leaf >= 2. */
+int mxd_tree_shape(uint64_t size, uint64_t chunk, uint64_t leaf, uint64_t* counts, int max_levels); /* returns #levels */
+int mxd_tree_digest(mxd_ctx*, const void* data /*host or device*/, uint64_t size, uint64_t chunk, uint64_t leaf,
+                    uint8_t* chunk_digests /*nchunks*32, may be NULL*/, uint64_t* nchunks, uint8_t root[32]);
+int mxd_tree_digest_file(mxd_ctx*, const char* path, uint64_t chunk, uint64_t leaf,
+                         uint8_t* chunk_digests, uint64_t cap_chunks, uint64_t* nchunks, uint64_t* size, uint8_t root[32]);
+/* Sharded form (one process per GPU): chunk digests of a piece that starts on a chunk boundary... */
+int mxd_tree_chunks(mxd_ctx*, const void* piece /*host or device*/, uint64_t nbytes, uint64_t chunk, uint64_t leaf,
+                    uint8_t* chunk_digests /*ceil(nbytes/chunk)*32 (>=1)*/);
+/* ...and the levels above the gathered chunk list (the only step after the all-gather). */
+int mxd_tree_finish(mxd_ctx*, const uint8_t* chunk_digests, uint64_t nchunks, uint64_t size, uint64_t chunk,
+                    uint64_t leaf, uint8_t root[32]);
+
+/* ---- multipart split: integer-only, bit-exact with the reference ------------------------- */
+int     mxd_calc_parts(int64_t total, int64_t partscount, mxd_part* out /*partscount*/);   /* calcParts, extension_s3.go:99-112 */
+int64_t mxd_server_part_count(int64_t size, int force_multipart);                         /* store_s3.go:198-203,273-279 */
+
+/* ---- digest strings (go-digest v1.0.0; registry.go:218-227 BlobDigestFun accepts only this form) */
+void mxd_digest_string(const uint8_t d[32], char out[72]);      /* "sha256:" + 64 lower hex + NUL */
+int  mxd_digest_parse(const char* s, uint8_t out[32]);          /* MXD_ERR_INVALID unless exactly that form */
+
+/* ---- pinned host memory for callers that want zero-copy H2D -------------------------------- */
+int  mxd_host_alloc(mxd_ctx*, void** out, uint64_t nbytes);
+void mxd_host_free(mxd_ctx*, void* p);
+int  mxd_host_register(mxd_ctx*, void* p, uint64_t nbytes);
+int  mxd_host_unregister(mxd_ctx*, void* p);
+
+/* ---- device-resident, asynchronous forms ---------------------------------------------------
+ * Inputs and outputs are device pointers on device `dev` (index into the context's device list);
+ * work is enqueued on `stream` (a cudaStream_t; NULL = the legacy default stream) and the call
+ * returns without synchronising.  Used by bench.py (kernel-only timing) and by callers that
+ * already hold blobs in HBM. */
+int mxd_dev_sha256_segments(mxd_ctx*, int dev, const void* d_data, uint64_t nbytes, uint64_t seg,
+                            void* d_out /*ceil(nbytes/seg)*32*/, void* stream);
+int mxd_dev_sha256_batch(mxd_ctx*, int dev, const mxd_span* d_spans /*device array*/, uint64_t n, void* d_out, void* stream);
+int mxd_dev_tree_chunks(mxd_ctx*, int dev, const void* d_piece, uint64_t nbytes, uint64_t chunk, uint64_t leaf,
+                        void* d_chunk_digests, void* stream);
+int mxd_dev_tree_finish(mxd_ctx*, int dev, const void* d_chunk_digests, uint64_t nchunks, uint64_t size,
+                        uint64_t chunk, uint64_t leaf, void* d_root /*32*/, void* stream);
+int mxd_dev_tree_digest(mxd_ctx*, int dev, const void* d_data, uint64_t size, uint64_t chunk, uint64_t leaf,
+                        void* d_chunk_digests /*may be NULL*/, void* d_root /*32*/, void* stream);
+int mxd_dev_compare(mxd_ctx*, int dev, const void* d_got, const void* d_want, uint64_t n, void* d_ok /*n bytes*/, void* stream);
+/* deterministic synthetic blob (benchmarks/tests): LE64 word j = splitmix64(seed, j); offset, n multiples of 8 */
+int mxd_dev_gen_fill(mxd_ctx*, int dev, void* d_dst, uint64_t offset, uint64_t n, uint64_t seed, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MODELX_DIGEST_H */

@@ -1,0 +1,118 @@
+"""ctypes binding of libmodelxdigest.so (the C ABI in include/modelx_digest.h).
+
+The shared library is built in-tree by ``__graft_entry__.build()`` (nvcc, sm_100a).  There is no
+Python or CPU implementation behind this module: if the library is missing, importing the symbols
+fails loudly, and if no CUDA device is present ``mxd_open`` returns MXD_ERR_NO_DEVICE.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmodelxdigest.so")
+
+MXD_OK = 0
+MXD_ERR_INVALID = -1
+MXD_ERR_NO_DEVICE = -2
+MXD_ERR_CUDA = -3
+MXD_ERR_IO = -4
+MXD_ERR_NOMEM = -5
+MXD_ERR_CANCELED = -6
+MXD_ERR_DIV_ZERO = -7
+
+
+class Span(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("len", C.c_uint64)]
+
+
+class Part(C.Structure):
+    _fields_ = [("offset", C.c_int64), ("length", C.c_int64)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("kernel_launches", C.c_uint64), ("bytes_hashed", C.c_uint64), ("h2d_bytes", C.c_uint64),
+                ("d2h_bytes", C.c_uint64), ("reserved", C.c_uint64 * 4)]
+
+
+u8p = C.POINTER(C.c_uint8)
+u64p = C.POINTER(C.c_uint64)
+vp = C.c_void_p
+
+# name -> (restype, argtypes); mirrors include/modelx_digest.h one to one
+PROTOTYPES = {
+    "mxd_open": (C.c_int, [C.POINTER(vp), C.POINTER(C.c_int), C.c_int, C.c_uint64]),
+    "mxd_close": (None, [vp]),
+    "mxd_device_count": (C.c_int, [vp]),
+    "mxd_cancel": (None, [vp]),
+    "mxd_reset_cancel": (None, [vp]),
+    "mxd_get_stats": (C.c_int, [vp, C.POINTER(Stats)]),
+    "mxd_strerror": (C.c_char_p, [C.c_int]),
+    "mxd_last_error": (C.c_char_p, []),
+    "mxd_abi_version": (C.c_int, []),
+    "mxd_sha256": (C.c_int, [vp, vp, C.c_uint64, u8p]),
+    "mxd_sha256_batch": (C.c_int, [vp, C.POINTER(Span), C.c_uint64, u8p]),
+    "mxd_sha256_file": (C.c_int, [vp, C.c_char_p, u8p, u64p]),
+    "mxd_sha256_files": (C.c_int, [vp, C.POINTER(C.c_char_p), C.c_uint64, u8p, u64p]),
+    "mxd_verify_batch": (C.c_int, [vp, C.POINTER(Span), u8p, C.c_uint64, u8p]),
+    "mxd_verify_files": (C.c_int, [vp, C.POINTER(C.c_char_p), u8p, C.c_uint64, u8p]),
+    "mxd_hasher_new": (C.c_int, [vp, C.POINTER(vp)]),
+    "mxd_hasher_write": (C.c_int, [vp, vp, C.c_uint64]),
+    "mxd_hasher_sum": (C.c_int, [vp, u8p]),
+    "mxd_hasher_reset": (C.c_int, [vp]),
+    "mxd_hasher_size": (C.c_uint64, [vp]),
+    "mxd_hasher_free": (None, [vp]),
+    "mxd_tree_shape": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, u64p, C.c_int]),
+    "mxd_tree_digest": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, C.c_uint64, u8p, u64p, u8p]),
+    "mxd_tree_digest_file": (C.c_int, [vp, C.c_char_p, C.c_uint64, C.c_uint64, u8p, C.c_uint64, u64p, u64p, u8p]),
+    "mxd_tree_chunks": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, C.c_uint64, u8p]),
+    "mxd_tree_finish": (C.c_int, [vp, u8p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, u8p]),
+    "mxd_calc_parts": (C.c_int, [C.c_int64, C.c_int64, C.POINTER(Part)]),
+    "mxd_server_part_count": (C.c_int64, [C.c_int64, C.c_int]),
+    "mxd_digest_string": (None, [u8p, C.c_char_p]),
+    "mxd_digest_parse": (C.c_int, [C.c_char_p, u8p]),
+    "mxd_host_alloc": (C.c_int, [vp, C.POINTER(vp), C.c_uint64]),
+    "mxd_host_free": (None, [vp, vp]),
+    "mxd_host_register": (C.c_int, [vp, vp, C.c_uint64]),
+    "mxd_host_unregister": (C.c_int, [vp, vp]),
+    "mxd_dev_sha256_segments": (C.c_int, [vp, C.c_int, vp, C.c_uint64, C.c_uint64, vp, vp]),
+    "mxd_dev_sha256_batch": (C.c_int, [vp, C.c_int, vp, C.c_uint64, vp, vp]),
+    "mxd_dev_tree_chunks": (C.c_int, [vp, C.c_int, vp, C.c_uint64, C.c_uint64, C.c_uint64, vp, vp]),
+    "mxd_dev_tree_finish": (C.c_int, [vp, C.c_int, vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, vp, vp]),
+    "mxd_dev_tree_digest": (C.c_int, [vp, C.c_int, vp, C.c_uint64, C.c_uint64, C.c_uint64, vp, vp, vp]),
+    "mxd_dev_compare": (C.c_int, [vp, C.c_int, vp, vp, C.c_uint64, vp, vp]),
+    "mxd_dev_gen_fill": (C.c_int, [vp, C.c_int, vp, C.c_uint64, C.c_uint64, C.c_uint64, vp]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the in-tree shared library and type every exported function."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). modelx_b200 has no pure-Python or CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError here means header and library disagree
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class MxdError(RuntimeError):
+    def __init__(self, status: int, where: str):
+        lib = load()
+        detail = lib.mxd_last_error().decode(errors="replace")
+        super().__init__(f"{where}: {lib.mxd_strerror(status).decode()} ({status}) {detail}")
+        self.status = status
+
+
+def check(status: int, where: str) -> None:
+    if status != MXD_OK:
+        raise MxdError(status, where)

@@ -1,0 +1,928 @@
+// C ABI of libmodelxdigest.so (include/modelx_digest.h): contexts, the pinned-host ring that
+// streams host/file data to the GPUs, tree assembly, and the integer split helpers.
+// Host side of the hot path of kubegems/modelx push/pull; each entry point cites the reference
+// call site it replaces in the header.  There is deliberately no CPU hashing in this file: if
+// CUDA is unavailable every digest call fails.
+#include "../../include/modelx_digest.h"
+#include "kernels.h"
+
+#include <atomic>
+#include <cerrno>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fcntl.h>
+#include <mutex>
+#include <string>
+#include <sys/stat.h>
+#include <thread>
+#include <unistd.h>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int status, const std::string& msg) {
+    g_last_error = msg;
+    return status;
+}
+
+#define MXD_CUDA(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            return fail(MXD_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));          \
+    } while (0)
+
+constexpr uint64_t kDefaultRingBytes = 256ull << 20;
+const uint32_t kIVHost[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au, 0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
+constexpr int kSlots = 4;
+
+struct DevState {
+    int ordinal = -1;
+    cudaStream_t compute = nullptr, copy = nullptr;
+    uint64_t slot_bytes = 0;
+    uint8_t* h_ring = nullptr;  // kSlots * slot_bytes, pinned
+    uint8_t* d_ring = nullptr;  // kSlots * slot_bytes
+    cudaEvent_t ev_copied[kSlots] = {}, ev_done[kSlots] = {};
+    uint8_t* h_small = nullptr;  // pinned scratch for small results / descriptors
+    uint64_t h_small_bytes = 0;
+    std::mutex mu;               // one streaming operation per device at a time
+};
+
+}  // namespace
+
+struct mxd_ctx {
+    std::vector<DevState*> devs;
+    std::atomic<uint64_t> launches{0}, bytes_hashed{0}, h2d{0}, d2h{0};
+    std::atomic<int> canceled{0};
+    std::atomic<uint32_t> rr{0};  // round-robin device pick for single-device calls
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int ordinal) { cudaGetDevice(&prev); cudaSetDevice(ordinal); }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+bool tree_params_ok(uint64_t chunk, uint64_t leaf) {
+    return leaf >= 64 && (leaf % 64) == 0 && chunk >= 2 * leaf && (chunk % leaf) == 0 && chunk / leaf <= 0xffffffffull;
+}
+
+// ---- kernel enqueue helpers ------------------------------------------------------------------
+int enqueue_segments(mxd_ctx* c, const uint8_t* d_data, uint64_t nbytes, uint64_t seg, uint8_t* d_out, cudaStream_t st) {
+    mxd::MsgJob j{};
+    j.base = d_data; j.nbytes = nbytes; j.seg = seg;
+    j.nmsg = nbytes ? (nbytes + seg - 1) / seg : 1;
+    j.out = d_out; j.finalize = 1; j.one = 1;
+    if (j.base == nullptr) {  // empty message: any non-null base keeps the kernel in segment mode
+        j.base = reinterpret_cast<const uint8_t*>(d_out);
+    }
+    MXD_CUDA(mxd::launch_sha256(j, st));
+    c->launches++; c->bytes_hashed += nbytes;
+    return MXD_OK;
+}
+
+// leaves -> chunk digests for one piece resident in device memory
+int enqueue_tree_chunks(mxd_ctx* c, const uint8_t* d_piece, uint64_t nbytes, uint64_t chunk, uint64_t leaf,
+                        uint8_t* d_chunks, cudaStream_t st) {
+    const uint64_t fanout = chunk / leaf;
+    const uint64_t n0 = nbytes ? (nbytes + leaf - 1) / leaf : 1;
+    uint8_t* ws = nullptr;
+    MXD_CUDA(cudaMallocAsync(&ws, n0 * 32, st));
+    int rc = enqueue_segments(c, d_piece, nbytes, leaf, ws, st);
+    if (rc == MXD_OK) rc = enqueue_segments(c, ws, n0 * 32, 32 * fanout, d_chunks, st);
+    cudaFreeAsync(ws, st);
+    return rc;
+}
+
+// levels above the chunk list, then the root message
+int enqueue_tree_finish(mxd_ctx* c, const uint8_t* d_chunks, uint64_t nchunks, uint64_t size, uint64_t chunk,
+                        uint64_t leaf, uint8_t* d_root, cudaStream_t st) {
+    const uint64_t fanout = chunk / leaf;
+    const uint8_t* cur = d_chunks;
+    uint64_t n = nchunks;
+    uint8_t* owned = nullptr;
+    int rc = MXD_OK;
+    while (n > 1 && rc == MXD_OK) {
+        const uint64_t nn = (n + fanout - 1) / fanout;
+        uint8_t* nxt = nullptr;
+        cudaError_t e = cudaMallocAsync(&nxt, nn * 32, st);
+        if (e != cudaSuccess) { rc = fail(MXD_ERR_CUDA, std::string("cudaMallocAsync: ") + cudaGetErrorString(e)); break; }
+        rc = enqueue_segments(c, cur, n * 32, 32 * fanout, nxt, st);
+        if (owned) cudaFreeAsync(owned, st);
+        owned = nxt; cur = nxt; n = nn;
+    }
+    if (rc == MXD_OK) {
+        cudaError_t e = mxd::launch_tree_root(size, leaf, (uint32_t)fanout, cur, d_root, st);
+        if (e != cudaSuccess) rc = fail(MXD_ERR_CUDA, std::string("launch_tree_root: ") + cudaGetErrorString(e));
+        else c->launches++;
+    }
+    if (owned) cudaFreeAsync(owned, st);
+    return rc;
+}
+
+enum class MemKind { Pageable, Pinned, Device };
+
+MemKind classify(const void* p, int* device_ordinal) {
+    cudaPointerAttributes a{};
+    if (p == nullptr || cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return MemKind::Pageable; }
+    if (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) {
+        if (device_ordinal) *device_ordinal = a.device;
+        return MemKind::Device;
+    }
+    if (a.type == cudaMemoryTypeHost) return MemKind::Pinned;
+    return MemKind::Pageable;
+}
+
+int dev_index_of(const mxd_ctx* c, int ordinal) {
+    for (size_t i = 0; i < c->devs.size(); ++i)
+        if (c->devs[i]->ordinal == ordinal) return (int)i;
+    return -1;
+}
+
+// ---- data sources for the streaming ring -------------------------------------------------------
+struct Source {
+    const uint8_t* mem = nullptr;  // host memory source
+    bool pinned = false;
+    int fd = -1;                   // file source
+    uint64_t base = 0;             // offset of this source's byte 0 inside the file
+};
+
+// Fill `n` bytes at logical offset `off` of the source into pinned `dst`; returns pointer the
+// H2D copy should read from (dst, or the caller's own memory when that is already pinned).
+int source_stage(const Source& s, uint64_t off, uint64_t n, uint8_t* dst, const uint8_t** from) {
+    if (s.fd >= 0) {
+        uint64_t got = 0;
+        while (got < n) {
+            ssize_t r = pread(s.fd, dst + got, n - got, (off_t)(s.base + off + got));
+            if (r < 0) { if (errno == EINTR) continue; return fail(MXD_ERR_IO, std::string("pread: ") + strerror(errno)); }
+            if (r == 0) return fail(MXD_ERR_IO, "pread: file shrank while hashing");
+            got += (uint64_t)r;
+        }
+        *from = dst;
+        return MXD_OK;
+    }
+    if (s.pinned) { *from = s.mem + off; return MXD_OK; }
+    memcpy(dst, s.mem + off, n);
+    *from = dst;
+    return MXD_OK;
+}
+
+// Stream [0, nbytes) of `src` through device `d`'s ring and hash it as uniform segments of `seg`
+// bytes into d_out (device, ceil(nbytes/seg) digests).  slot_bytes is a multiple of seg.
+// H2D copies run on the copy stream, kernels on the compute stream; a slot is refilled only
+// after the kernel that read it has finished, so copy k+1.. overlap kernel k.
+int stream_segments(mxd_ctx* c, DevState* d, const Source& src, uint64_t nbytes, uint64_t seg, uint8_t* d_out) {
+    const uint64_t per_slot = (d->slot_bytes / seg) * seg;
+    if (per_slot == 0) return fail(MXD_ERR_INVALID, "ring slot smaller than one segment; raise ring_bytes");
+    if (nbytes == 0) return enqueue_segments(c, nullptr, 0, seg, d_out, d->compute);
+    uint64_t off = 0;
+    for (uint64_t i = 0; off < nbytes; ++i) {
+        if (c->canceled.load()) return fail(MXD_ERR_CANCELED, "canceled");
+        const int s = (int)(i % kSlots);
+        const uint64_t n = (nbytes - off < per_slot) ? nbytes - off : per_slot;
+        if (i >= (uint64_t)kSlots) MXD_CUDA(cudaEventSynchronize(d->ev_done[s]));
+        uint8_t* h_slot = d->h_ring + (uint64_t)s * d->slot_bytes;
+        uint8_t* d_slot = d->d_ring + (uint64_t)s * d->slot_bytes;
+        const uint8_t* from = nullptr;
+        int rc = source_stage(src, off, n, h_slot, &from);
+        if (rc != MXD_OK) return rc;
+        MXD_CUDA(cudaMemcpyAsync(d_slot, from, n, cudaMemcpyHostToDevice, d->copy));
+        MXD_CUDA(cudaEventRecord(d->ev_copied[s], d->copy));
+        MXD_CUDA(cudaStreamWaitEvent(d->compute, d->ev_copied[s], 0));
+        rc = enqueue_segments(c, d_slot, n, seg, d_out + (off / seg) * 32, d->compute);
+        if (rc != MXD_OK) return rc;
+        MXD_CUDA(cudaEventRecord(d->ev_done[s], d->compute));
+        c->h2d += n;
+        off += n;
+    }
+    return MXD_OK;
+}
+
+// chunk digests of a host/file piece on one device; result left in device memory d_chunks
+int stream_tree_chunks(mxd_ctx* c, DevState* d, const Source& src, uint64_t nbytes, uint64_t chunk, uint64_t leaf,
+                       uint8_t* d_chunks) {
+    const uint64_t fanout = chunk / leaf;
+    const uint64_t n0 = nbytes ? (nbytes + leaf - 1) / leaf : 1;
+    uint8_t* d_leaves = nullptr;
+    MXD_CUDA(cudaMalloc(&d_leaves, n0 * 32));
+    int rc = stream_segments(c, d, src, nbytes, leaf, d_leaves);
+    if (rc == MXD_OK) rc = enqueue_segments(c, d_leaves, n0 * 32, 32 * fanout, d_chunks, d->compute);
+    if (rc == MXD_OK) {
+        cudaError_t e = cudaStreamSynchronize(d->compute);
+        if (e != cudaSuccess) rc = fail(MXD_ERR_CUDA, std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e));
+    } else {
+        cudaStreamSynchronize(d->compute);
+    }
+    cudaFree(d_leaves);
+    return rc;
+}
+
+// Chunk digests of a host/file blob using every device of the context: device g takes the
+// contiguous chunk range [g*n/G, (g+1)*n/G) (sequential reads per device, no data-path
+// collective).  Results land in host memory `out` (nchunks*32).
+int host_tree_chunks_all(mxd_ctx* c, const Source& src, uint64_t nbytes, uint64_t chunk, uint64_t leaf, uint8_t* out) {
+    const uint64_t nchunks = nbytes ? (nbytes + chunk - 1) / chunk : 1;
+    const int G = (int)std::min<uint64_t>(c->devs.size(), nchunks);
+    std::vector<int> rcs(G, MXD_OK);
+    std::vector<std::string> errs(G);
+    auto work = [&](int g) {
+        DevState* d = c->devs[g];
+        std::lock_guard<std::mutex> lk(d->mu);
+        DeviceGuard guard(d->ordinal);
+        const uint64_t c0 = nchunks * g / G, c1 = nchunks * (g + 1) / G;
+        const uint64_t b0 = c0 * chunk, b1 = std::min<uint64_t>(c1 * chunk, nbytes);
+        Source piece = src;
+        if (piece.fd >= 0) piece.base += b0; else piece.mem += b0;
+        uint8_t* d_chunks = nullptr;
+        cudaError_t e = cudaMalloc(&d_chunks, (c1 - c0) * 32);
+        if (e != cudaSuccess) { rcs[g] = MXD_ERR_CUDA; errs[g] = cudaGetErrorString(e); return; }
+        int rc = stream_tree_chunks(c, d, piece, b1 - b0, chunk, leaf, d_chunks);
+        if (rc == MXD_OK) {
+            e = cudaMemcpy(out + c0 * 32, d_chunks, (c1 - c0) * 32, cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) { rc = MXD_ERR_CUDA; g_last_error = cudaGetErrorString(e); }
+            c->d2h += (c1 - c0) * 32;
+        }
+        cudaFree(d_chunks);
+        rcs[g] = rc;
+        if (rc != MXD_OK) errs[g] = g_last_error;
+    };
+    if (G == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int g = 0; g < G; ++g) th.emplace_back(work, g);
+        for (auto& t : th) t.join();
+    }
+    for (int g = 0; g < G; ++g)
+        if (rcs[g] != MXD_OK) return fail(rcs[g], errs[g]);
+    return MXD_OK;
+}
+
+// upper levels + root from a host-resident chunk list (tiny: 32 B per chunk)
+int host_tree_finish(mxd_ctx* c, DevState* d, const uint8_t* chunks, uint64_t nchunks, uint64_t size, uint64_t chunk,
+                     uint64_t leaf, uint8_t root[32]) {
+    std::lock_guard<std::mutex> lk(d->mu);
+    DeviceGuard guard(d->ordinal);
+    uint8_t* d_buf = nullptr;
+    MXD_CUDA(cudaMalloc(&d_buf, nchunks * 32 + 32));
+    int rc = MXD_OK;
+    cudaError_t e = cudaMemcpyAsync(d_buf, chunks, nchunks * 32, cudaMemcpyHostToDevice, d->compute);
+    if (e != cudaSuccess) rc = fail(MXD_ERR_CUDA, cudaGetErrorString(e));
+    if (rc == MXD_OK) rc = enqueue_tree_finish(c, d_buf, nchunks, size, chunk, leaf, d_buf + nchunks * 32, d->compute);
+    if (rc == MXD_OK) {
+        e = cudaMemcpyAsync(root, d_buf + nchunks * 32, 32, cudaMemcpyDeviceToHost, d->compute);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(d->compute);
+        if (e != cudaSuccess) rc = fail(MXD_ERR_CUDA, cudaGetErrorString(e));
+        c->h2d += nchunks * 32; c->d2h += 32;
+    } else {
+        cudaStreamSynchronize(d->compute);
+    }
+    cudaFree(d_buf);
+    return rc;
+}
+
+DevState* pick_device(mxd_ctx* c) { return c->devs[c->rr++ % c->devs.size()]; }
+
+// ---- lock-step hashing of n whole messages from host sources (files or host spans) -------------
+// Round k moves bytes [k*S, (k+1)*S) of every still-running message into one ring slot
+// (message i at slot offset i*S) and advances all chains together; each lane carries its chain
+// state in device memory between rounds.  This is the reference's one-digest-per-file result
+// (push.go:149-161) for many files at once.
+struct LockstepInput {
+    std::vector<Source> src;
+    std::vector<uint64_t> len;
+};
+
+int lockstep_digest(mxd_ctx* c, DevState* d, const LockstepInput& in, uint8_t* out) {
+    const uint64_t n = in.src.size();
+    if (n == 0) return MXD_OK;
+    std::lock_guard<std::mutex> lk(d->mu);
+    DeviceGuard guard(d->ordinal);
+    uint64_t S = (d->slot_bytes / n) & ~63ull;
+    if (S == 0) return fail(MXD_ERR_INVALID, "too many messages for the ring slot; raise ring_bytes or split the batch");
+    if (S > (8ull << 20)) S = 8ull << 20;
+    uint64_t maxlen = 0;
+    for (uint64_t i = 0; i < n; ++i) maxlen = std::max(maxlen, in.len[i]);
+    const uint64_t rounds = std::max<uint64_t>(1, (maxlen + S - 1) / S);
+
+    // per-round descriptors live in pinned memory, double-buffered per slot
+    const uint64_t desc_bytes = n * (sizeof(mxd::DevSpan) + sizeof(uint64_t) + 1);
+    uint8_t *h_desc = nullptr, *d_desc = nullptr, *d_out = nullptr;
+    uint32_t* d_state = nullptr;
+    MXD_CUDA(cudaMallocHost(&h_desc, desc_bytes * kSlots));
+    int rc = MXD_OK;
+    cudaError_t e;
+    if ((e = cudaMalloc(&d_desc, desc_bytes * kSlots)) != cudaSuccess ||
+        (e = cudaMalloc(&d_out, n * 32)) != cudaSuccess || (e = cudaMalloc(&d_state, n * 32)) != cudaSuccess) {
+        rc = fail(MXD_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    }
+    if (rc == MXD_OK) {  // every chain starts from the FIPS 180-4 initial hash value
+        std::vector<uint32_t> iv(n * 8);
+        for (uint64_t i = 0; i < n; ++i) memcpy(&iv[8 * i], kIVHost, 32);
+        e = cudaMemcpy(d_state, iv.data(), n * 32, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) rc = fail(MXD_ERR_CUDA, cudaGetErrorString(e));
+    }
+    for (uint64_t k = 0; k < rounds && rc == MXD_OK; ++k) {
+        if (c->canceled.load()) { rc = fail(MXD_ERR_CANCELED, "canceled"); break; }
+        const int s = (int)(k % kSlots);
+        if (k >= (uint64_t)kSlots) {
+            e = cudaEventSynchronize(d->ev_done[s]);
+            if (e != cudaSuccess) { rc = fail(MXD_ERR_CUDA, cudaGetErrorString(e)); break; }
+        }
+        uint8_t* h_slot = d->h_ring + (uint64_t)s * d->slot_bytes;
+        uint8_t* d_slot = d->d_ring + (uint64_t)s * d->slot_bytes;
+        uint8_t* hd = h_desc + desc_bytes * s;
+        auto* spans = reinterpret_cast<mxd::DevSpan*>(hd);
+        auto* prefix = reinterpret_cast<uint64_t*>(hd + n * sizeof(mxd::DevSpan));
+        uint8_t* ctl = hd + n * (sizeof(mxd::DevSpan) + sizeof(uint64_t));
+        uint64_t moved = 0;
+        for (uint64_t i = 0; i < n && rc == MXD_OK; ++i) {
+            // message i ends in round k_fin; it is finalised there and skipped afterwards
+            const uint64_t L = in.len[i];
+            const uint64_t k_fin = L ? (L - 1) / S : 0;
+            if (k > k_fin) { spans[i] = {d_slot, 0}; prefix[i] = L; ctl[i] = 2; continue; }
+            const uint64_t done = k * S;
+            const uint64_t take = std::min(L - done, S);
+            const bool last = (k == k_fin);
+            const uint8_t* from = nullptr;
+            if (take) {
+                Source one = in.src[i];
+                one.pinned = false;  // gather into the slot so the whole round is one H2D copy
+                rc = source_stage(one, done, take, h_slot + i * S, &from);
+            }
+            spans[i] = {d_slot + i * S, take};
+            prefix[i] = done;
+            ctl[i] = last ? 1 : 0;
+            moved += take;
+        }
+        if (rc != MXD_OK) break;
+        const uint64_t span_bytes = n * S;
+        e = cudaMemcpyAsync(d_slot, h_slot, span_bytes, cudaMemcpyHostToDevice, d->copy);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_desc + desc_bytes * s, hd, desc_bytes, cudaMemcpyHostToDevice, d->copy);
+        if (e == cudaSuccess) e = cudaEventRecord(d->ev_copied[s], d->copy);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(d->compute, d->ev_copied[s], 0);
+        if (e != cudaSuccess) { rc = fail(MXD_ERR_CUDA, cudaGetErrorString(e)); break; }
+        mxd::MsgJob j{};
+        uint8_t* dd = d_desc + desc_bytes * s;
+        j.spans = dd; j.nmsg = n; j.out = d_out; j.state = d_state;
+        j.prefix = reinterpret_cast<const uint64_t*>(dd + n * sizeof(mxd::DevSpan));
+        j.ctl = dd + n * (sizeof(mxd::DevSpan) + sizeof(uint64_t));
+        j.finalize = 0; j.one = 1;
+        e = mxd::launch_sha256(j, d->compute);
+        if (e == cudaSuccess) e = cudaEventRecord(d->ev_done[s], d->compute);
+        if (e != cudaSuccess) { rc = fail(MXD_ERR_CUDA, cudaGetErrorString(e)); break; }
+        c->launches++; c->bytes_hashed += moved; c->h2d += span_bytes + desc_bytes;
+    }
+    if (rc == MXD_OK) {
+        e = cudaStreamSynchronize(d->compute);
+        if (e == cudaSuccess) e = cudaMemcpy(out, d_out, n * 32, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = fail(MXD_ERR_CUDA, cudaGetErrorString(e));
+        c->d2h += n * 32;
+    } else {
+        cudaStreamSynchronize(d->compute); cudaStreamSynchronize(d->copy);
+    }
+    cudaFree(d_state); cudaFree(d_out); cudaFree(d_desc); cudaFreeHost(h_desc);
+    return rc;
+}
+
+int open_files(const char* const* paths, uint64_t n, LockstepInput* in, std::vector<int>* fds) {
+    in->src.resize(n); in->len.resize(n);
+    for (uint64_t i = 0; i < n; ++i) {
+        int fd = open(paths[i], O_RDONLY | O_CLOEXEC);
+        if (fd < 0) { int e = errno; for (int f : *fds) close(f); fds->clear(); errno = e;
+                      return fail(MXD_ERR_IO, std::string("open ") + paths[i] + ": " + strerror(e)); }
+        fds->push_back(fd);
+        struct stat st;
+        if (fstat(fd, &st) != 0) { int e = errno; for (int f : *fds) close(f); fds->clear(); errno = e;
+                                   return fail(MXD_ERR_IO, std::string("fstat ") + paths[i] + ": " + strerror(e)); }
+        in->src[i].fd = fd; in->len[i] = (uint64_t)st.st_size;
+    }
+    return MXD_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int mxd_abi_version(void) { return MXD_ABI_VERSION; }
+
+const char* mxd_strerror(int status) {
+    switch (status) {
+        case MXD_OK: return "ok";
+        case MXD_ERR_INVALID: return "invalid argument";
+        case MXD_ERR_NO_DEVICE: return "no CUDA device available (modelx-b200 has no CPU fallback)";
+        case MXD_ERR_CUDA: return "CUDA error";
+        case MXD_ERR_IO: return "I/O error";
+        case MXD_ERR_NOMEM: return "out of memory";
+        case MXD_ERR_CANCELED: return "canceled";
+        case MXD_ERR_DIV_ZERO: return "integer divide by zero (calcParts with 0 parts)";
+        default: return "unknown status";
+    }
+}
+
+const char* mxd_last_error(void) { return g_last_error.c_str(); }
+
+int mxd_open(mxd_ctx** out, const int* devices, int ndev, uint64_t ring_bytes) {
+    if (!out || ndev < 0 || (ndev > 0 && !devices)) return fail(MXD_ERR_INVALID, "mxd_open: bad arguments");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(MXD_ERR_NO_DEVICE, std::string("cudaGetDeviceCount: ") + (e == cudaSuccess ? "0 devices" : cudaGetErrorString(e)));
+    }
+    std::vector<int> ords;
+    if (ndev == 0) for (int i = 0; i < count; ++i) ords.push_back(i);
+    else for (int i = 0; i < ndev; ++i) {
+        if (devices[i] < 0 || devices[i] >= count) return fail(MXD_ERR_INVALID, "mxd_open: device ordinal out of range");
+        ords.push_back(devices[i]);
+    }
+    if (const char* env = getenv("MXD_RING_BYTES")) { uint64_t v = strtoull(env, nullptr, 10); if (v) ring_bytes = v; }
+    if (ring_bytes == 0) ring_bytes = kDefaultRingBytes;
+    uint64_t slot = (ring_bytes / kSlots) & ~((1ull << 20) - 1);
+    if (slot < (1ull << 20)) slot = 1ull << 20;
+
+    auto* c = new mxd_ctx();
+    int prev = -1; cudaGetDevice(&prev);
+    int rc = MXD_OK;
+    for (int ord : ords) {
+        auto* d = new DevState();
+        d->ordinal = ord; d->slot_bytes = slot;
+        c->devs.push_back(d);
+        if ((e = cudaSetDevice(ord)) != cudaSuccess) break;
+        if ((e = cudaStreamCreateWithFlags(&d->compute, cudaStreamNonBlocking)) != cudaSuccess) break;
+        if ((e = cudaStreamCreateWithFlags(&d->copy, cudaStreamNonBlocking)) != cudaSuccess) break;
+        if ((e = cudaHostAlloc(&d->h_ring, slot * kSlots, cudaHostAllocPortable)) != cudaSuccess) break;
+        if ((e = cudaMalloc(&d->d_ring, slot * kSlots)) != cudaSuccess) break;
+        d->h_small_bytes = 1 << 20;
+        if ((e = cudaHostAlloc(&d->h_small, d->h_small_bytes, cudaHostAllocPortable)) != cudaSuccess) break;
+        for (int s = 0; s < kSlots && e == cudaSuccess; ++s) {
+            e = cudaEventCreateWithFlags(&d->ev_copied[s], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_done[s], cudaEventDisableTiming);
+        }
+        if (e != cudaSuccess) break;
+        // keep stream-ordered workspace allocations cached instead of returning them to the OS
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, ord) == cudaSuccess) {
+            uint64_t keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
+    if (prev >= 0) cudaSetDevice(prev);
+    if (e != cudaSuccess) {
+        rc = fail(MXD_ERR_CUDA, std::string("mxd_open: ") + cudaGetErrorString(e));
+        mxd_close(c);
+        return rc;
+    }
+    *out = c;
+    return MXD_OK;
+}
+
+void mxd_close(mxd_ctx* c) {
+    if (!c) return;
+    int prev = -1; cudaGetDevice(&prev);
+    for (DevState* d : c->devs) {
+        if (d->ordinal >= 0) cudaSetDevice(d->ordinal);
+        if (d->compute) { cudaStreamSynchronize(d->compute); cudaStreamDestroy(d->compute); }
+        if (d->copy) { cudaStreamSynchronize(d->copy); cudaStreamDestroy(d->copy); }
+        for (int s = 0; s < kSlots; ++s) {
+            if (d->ev_copied[s]) cudaEventDestroy(d->ev_copied[s]);
+            if (d->ev_done[s]) cudaEventDestroy(d->ev_done[s]);
+        }
+        if (d->h_ring) cudaFreeHost(d->h_ring);
+        if (d->d_ring) cudaFree(d->d_ring);
+        if (d->h_small) cudaFreeHost(d->h_small);
+        delete d;
+    }
+    if (prev >= 0) cudaSetDevice(prev);
+    delete c;
+}
+
+int mxd_device_count(const mxd_ctx* c) { return c ? (int)c->devs.size() : 0; }
+void mxd_cancel(mxd_ctx* c) { if (c) c->canceled.store(1); }
+void mxd_reset_cancel(mxd_ctx* c) { if (c) c->canceled.store(0); }
+
+int mxd_get_stats(const mxd_ctx* c, mxd_stats* out) {
+    if (!c || !out) return fail(MXD_ERR_INVALID, "mxd_get_stats: null");
+    memset(out, 0, sizeof *out);
+    out->kernel_launches = c->launches.load(); out->bytes_hashed = c->bytes_hashed.load();
+    out->h2d_bytes = c->h2d.load(); out->d2h_bytes = c->d2h.load();
+    return MXD_OK;
+}
+
+// ---- integer split: extension_s3.go:99-112, store_s3.go:198-203,273-279 --------------------------
+int mxd_calc_parts(int64_t total, int64_t partscount, mxd_part* out) {
+    if (partscount == 0) return fail(MXD_ERR_DIV_ZERO, "calcParts: partscount == 0 (reference panics: integer divide by zero)");
+    if (partscount < 0 || !out) return fail(MXD_ERR_INVALID, "calcParts: negative part count");
+    const int64_t partsize = total / partscount;
+    for (int64_t i = 0; i < partscount; ++i) {
+        out[i].offset = i * partsize;
+        out[i].length = (i == partscount - 1) ? total - out[i].offset : partsize;
+    }
+    return MXD_OK;
+}
+
+int64_t mxd_server_part_count(int64_t size, int force_multipart) {
+    const int64_t kThreshold = 5ll << 30;   // MultiPartUploadThreshold
+    const int64_t kDefaultParts = 3;        // DefaultPartCount
+    if (!force_multipart && size <= kThreshold) return 1;
+    int64_t count = size / kThreshold;
+    if (count == 0) return kDefaultParts;
+    return (size % kThreshold) ? count + 1 : count;
+}
+
+// ---- digest strings -------------------------------------------------------------------------------
+void mxd_digest_string(const uint8_t d[32], char out[72]) {
+    static const char* hex = "0123456789abcdef";
+    memcpy(out, "sha256:", 7);
+    for (int i = 0; i < 32; ++i) { out[7 + 2 * i] = hex[d[i] >> 4]; out[8 + 2 * i] = hex[d[i] & 15]; }
+    out[71] = 0;
+}
+
+int mxd_digest_parse(const char* s, uint8_t out[32]) {
+    if (!s || strncmp(s, "sha256:", 7) != 0 || strlen(s) != 71) return fail(MXD_ERR_INVALID, "digest: want sha256:<64 lower hex>");
+    for (int i = 0; i < 32; ++i) {
+        int v = 0;
+        for (int k = 0; k < 2; ++k) {
+            const char ch = s[7 + 2 * i + k];
+            int x = (ch >= '0' && ch <= '9') ? ch - '0' : (ch >= 'a' && ch <= 'f') ? ch - 'a' + 10 : -1;
+            if (x < 0) return fail(MXD_ERR_INVALID, "digest: invalid hex (go-digest accepts lower case only)");
+            v = v * 16 + x;
+        }
+        if (out) out[i] = (uint8_t)v;
+    }
+    return MXD_OK;
+}
+
+// ---- tree ---------------------------------------------------------------------------------------------
+int mxd_tree_shape(uint64_t size, uint64_t chunk, uint64_t leaf, uint64_t* counts, int max_levels) {
+    if (!tree_params_ok(chunk, leaf) || !counts || max_levels < 2) return fail(MXD_ERR_INVALID, "tree: bad chunk/leaf");
+    const uint64_t fanout = chunk / leaf;
+    uint64_t n = size ? (size + leaf - 1) / leaf : 1;
+    int lv = 0;
+    counts[lv++] = n;
+    do {
+        if (lv >= max_levels) return fail(MXD_ERR_INVALID, "tree: too many levels for counts[]");
+        n = (n + fanout - 1) / fanout;
+        counts[lv++] = n;
+    } while (n > 1);
+    return lv;
+}
+
+int mxd_dev_sha256_segments(mxd_ctx* c, int dev, const void* d_data, uint64_t nbytes, uint64_t seg, void* d_out, void* stream) {
+    if (!c || dev < 0 || dev >= (int)c->devs.size() || seg == 0 || !d_out) return fail(MXD_ERR_INVALID, "dev_sha256_segments: bad arguments");
+    DeviceGuard guard(c->devs[dev]->ordinal);
+    return enqueue_segments(c, static_cast<const uint8_t*>(d_data), nbytes, seg, static_cast<uint8_t*>(d_out), (cudaStream_t)stream);
+}
+
+int mxd_dev_sha256_batch(mxd_ctx* c, int dev, const mxd_span* d_spans, uint64_t n, void* d_out, void* stream) {
+    if (!c || dev < 0 || dev >= (int)c->devs.size() || (n && (!d_spans || !d_out))) return fail(MXD_ERR_INVALID, "dev_sha256_batch: bad arguments");
+    if (n == 0) return MXD_OK;
+    DeviceGuard guard(c->devs[dev]->ordinal);
+    mxd::MsgJob j{};
+    j.spans = d_spans; j.nmsg = n; j.out = static_cast<uint8_t*>(d_out); j.finalize = 1; j.one = 1;
+    MXD_CUDA(mxd::launch_sha256(j, (cudaStream_t)stream));
+    c->launches++;
+    return MXD_OK;
+}
+
+int mxd_dev_tree_chunks(mxd_ctx* c, int dev, const void* d_piece, uint64_t nbytes, uint64_t chunk, uint64_t leaf,
+                        void* d_chunk_digests, void* stream) {
+    if (!c || dev < 0 || dev >= (int)c->devs.size() || !tree_params_ok(chunk, leaf) || !d_chunk_digests)
+        return fail(MXD_ERR_INVALID, "dev_tree_chunks: bad arguments");
+    DeviceGuard guard(c->devs[dev]->ordinal);
+    return enqueue_tree_chunks(c, static_cast<const uint8_t*>(d_piece), nbytes, chunk, leaf,
+                               static_cast<uint8_t*>(d_chunk_digests), (cudaStream_t)stream);
+}
+
+int mxd_dev_tree_finish(mxd_ctx* c, int dev, const void* d_chunk_digests, uint64_t nchunks, uint64_t size, uint64_t chunk,
+                        uint64_t leaf, void* d_root, void* stream) {
+    if (!c || dev < 0 || dev >= (int)c->devs.size() || !tree_params_ok(chunk, leaf) || !d_chunk_digests || !d_root || nchunks == 0)
+        return fail(MXD_ERR_INVALID, "dev_tree_finish: bad arguments");
+    DeviceGuard guard(c->devs[dev]->ordinal);
+    return enqueue_tree_finish(c, static_cast<const uint8_t*>(d_chunk_digests), nchunks, size, chunk, leaf,
+                               static_cast<uint8_t*>(d_root), (cudaStream_t)stream);
+}
+
+int mxd_dev_tree_digest(mxd_ctx* c, int dev, const void* d_data, uint64_t size, uint64_t chunk, uint64_t leaf,
+                        void* d_chunk_digests, void* d_root, void* stream) {
+    if (!c || dev < 0 || dev >= (int)c->devs.size() || !tree_params_ok(chunk, leaf) || !d_root)
+        return fail(MXD_ERR_INVALID, "dev_tree_digest: bad arguments");
+    DeviceGuard guard(c->devs[dev]->ordinal);
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint64_t nchunks = size ? (size + chunk - 1) / chunk : 1;
+    uint8_t* chunks = static_cast<uint8_t*>(d_chunk_digests);
+    uint8_t* owned = nullptr;
+    if (!chunks) { MXD_CUDA(cudaMallocAsync(&owned, nchunks * 32, st)); chunks = owned; }
+    int rc = enqueue_tree_chunks(c, static_cast<const uint8_t*>(d_data), size, chunk, leaf, chunks, st);
+    if (rc == MXD_OK) rc = enqueue_tree_finish(c, chunks, nchunks, size, chunk, leaf, static_cast<uint8_t*>(d_root), st);
+    if (owned) cudaFreeAsync(owned, st);
+    return rc;
+}
+
+int mxd_dev_compare(mxd_ctx* c, int dev, const void* d_got, const void* d_want, uint64_t n, void* d_ok, void* stream) {
+    if (!c || dev < 0 || dev >= (int)c->devs.size() || (n && (!d_got || !d_want || !d_ok))) return fail(MXD_ERR_INVALID, "dev_compare: bad arguments");
+    DeviceGuard guard(c->devs[dev]->ordinal);
+    MXD_CUDA(mxd::launch_compare(static_cast<const uint8_t*>(d_got), static_cast<const uint8_t*>(d_want), n,
+                                 static_cast<uint8_t*>(d_ok), (cudaStream_t)stream));
+    if (n) c->launches++;
+    return MXD_OK;
+}
+
+int mxd_dev_gen_fill(mxd_ctx* c, int dev, void* d_dst, uint64_t offset, uint64_t n, uint64_t seed, void* stream) {
+    if (!c || dev < 0 || dev >= (int)c->devs.size() || (n && !d_dst)) return fail(MXD_ERR_INVALID, "dev_gen_fill: bad arguments");
+    DeviceGuard guard(c->devs[dev]->ordinal);
+    MXD_CUDA(mxd::launch_gen_fill(d_dst, offset, n, seed, (cudaStream_t)stream));
+    if (n) c->launches++;
+    return MXD_OK;
+}
+
+int mxd_tree_chunks(mxd_ctx* c, const void* piece, uint64_t nbytes, uint64_t chunk, uint64_t leaf, uint8_t* out) {
+    if (!c || !tree_params_ok(chunk, leaf) || !out || (nbytes && !piece)) return fail(MXD_ERR_INVALID, "tree_chunks: bad arguments");
+    const uint64_t nchunks = nbytes ? (nbytes + chunk - 1) / chunk : 1;
+    int ord = -1;
+    const MemKind kind = classify(piece, &ord);
+    if (kind == MemKind::Device) {
+        const int di = dev_index_of(c, ord);
+        if (di < 0) return fail(MXD_ERR_INVALID, "tree_chunks: data lives on a device this context does not drive");
+        DevState* d = c->devs[di];
+        std::lock_guard<std::mutex> lk(d->mu);
+        DeviceGuard guard(d->ordinal);
+        uint8_t* d_chunks = nullptr;
+        MXD_CUDA(cudaMalloc(&d_chunks, nchunks * 32));
+        int rc = enqueue_tree_chunks(c, static_cast<const uint8_t*>(piece), nbytes, chunk, leaf, d_chunks, d->compute);
+        if (rc == MXD_OK) {
+            cudaError_t e = cudaMemcpyAsync(out, d_chunks, nchunks * 32, cudaMemcpyDeviceToHost, d->compute);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(d->compute);
+            if (e != cudaSuccess) rc = fail(MXD_ERR_CUDA, cudaGetErrorString(e));
+            c->d2h += nchunks * 32;
+        }
+        cudaFree(d_chunks);
+        return rc;
+    }
+    Source src; src.mem = static_cast<const uint8_t*>(piece); src.pinned = (kind == MemKind::Pinned);
+    return host_tree_chunks_all(c, src, nbytes, chunk, leaf, out);
+}
+
+int mxd_tree_finish(mxd_ctx* c, const uint8_t* chunk_digests, uint64_t nchunks, uint64_t size, uint64_t chunk,
+                    uint64_t leaf, uint8_t root[32]) {
+    if (!c || !tree_params_ok(chunk, leaf) || !chunk_digests || !root || nchunks == 0) return fail(MXD_ERR_INVALID, "tree_finish: bad arguments");
+    const uint64_t expect = size ? (size + chunk - 1) / chunk : 1;
+    if (expect != nchunks) return fail(MXD_ERR_INVALID, "tree_finish: nchunks does not match size/chunk");
+    return host_tree_finish(c, c->devs[0], chunk_digests, nchunks, size, chunk, leaf, root);
+}
+
+int mxd_tree_digest(mxd_ctx* c, const void* data, uint64_t size, uint64_t chunk, uint64_t leaf, uint8_t* chunk_digests,
+                    uint64_t* nchunks_out, uint8_t root[32]) {
+    if (!c || !tree_params_ok(chunk, leaf) || !root || (size && !data)) return fail(MXD_ERR_INVALID, "tree_digest: bad arguments");
+    const uint64_t nchunks = size ? (size + chunk - 1) / chunk : 1;
+    std::vector<uint8_t> tmp;
+    uint8_t* chunks = chunk_digests;
+    if (!chunks) { tmp.resize(nchunks * 32); chunks = tmp.data(); }
+    int rc = mxd_tree_chunks(c, data, size, chunk, leaf, chunks);
+    if (rc != MXD_OK) return rc;
+    if (nchunks_out) *nchunks_out = nchunks;
+    return host_tree_finish(c, c->devs[0], chunks, nchunks, size, chunk, leaf, root);
+}
+
+int mxd_tree_digest_file(mxd_ctx* c, const char* path, uint64_t chunk, uint64_t leaf, uint8_t* chunk_digests,
+                         uint64_t cap_chunks, uint64_t* nchunks_out, uint64_t* size_out, uint8_t root[32]) {
+    if (!c || !path || !tree_params_ok(chunk, leaf) || !root) return fail(MXD_ERR_INVALID, "tree_digest_file: bad arguments");
+    int fd = open(path, O_RDONLY | O_CLOEXEC);
+    if (fd < 0) return fail(MXD_ERR_IO, std::string("open ") + path + ": " + strerror(errno));
+    struct stat st;
+    if (fstat(fd, &st) != 0) { int e = errno; close(fd); errno = e; return fail(MXD_ERR_IO, std::string("fstat: ") + strerror(e)); }
+    const uint64_t size = (uint64_t)st.st_size;
+    const uint64_t nchunks = size ? (size + chunk - 1) / chunk : 1;
+    if (size_out) *size_out = size;
+    if (nchunks_out) *nchunks_out = nchunks;
+    if (chunk_digests && cap_chunks < nchunks) { close(fd); return fail(MXD_ERR_INVALID, "tree_digest_file: chunk_digests too small"); }
+    std::vector<uint8_t> tmp;
+    uint8_t* chunks = chunk_digests;
+    if (!chunks) { tmp.resize(nchunks * 32); chunks = tmp.data(); }
+    Source src; src.fd = fd;
+    int rc = host_tree_chunks_all(c, src, size, chunk, leaf, chunks);
+    close(fd);
+    if (rc != MXD_OK) return rc;
+    return host_tree_finish(c, c->devs[0], chunks, nchunks, size, chunk, leaf, root);
+}
+
+// ---- whole-message digests ---------------------------------------------------------------------------
+int mxd_sha256_batch(mxd_ctx* c, const mxd_span* spans, uint64_t n, uint8_t* out) {
+    if (!c || (n && (!spans || !out))) return fail(MXD_ERR_INVALID, "sha256_batch: bad arguments");
+    if (n == 0) return MXD_OK;
+    // device-resident spans: one launch, no staging
+    int ord = -1, first_ord = -1;
+    bool all_dev = true, any_dev = false;
+    for (uint64_t i = 0; i < n; ++i) {
+        if (spans[i].len && !spans[i].ptr) return fail(MXD_ERR_INVALID, "sha256_batch: null span with non-zero length");
+        if (spans[i].len == 0) continue;
+        if (classify(spans[i].ptr, &ord) == MemKind::Device) {
+            any_dev = true;
+            if (first_ord < 0) first_ord = ord; else if (ord != first_ord) return fail(MXD_ERR_INVALID, "sha256_batch: spans on different devices");
+        } else all_dev = false;
+    }
+    if (any_dev && !all_dev) return fail(MXD_ERR_INVALID, "sha256_batch: mixing host and device spans");
+    if (any_dev) {
+        const int di = dev_index_of(c, first_ord);
+        if (di < 0) return fail(MXD_ERR_INVALID, "sha256_batch: data lives on a device this context does not drive");
+        DevState* d = c->devs[di];
+        std::lock_guard<std::mutex> lk(d->mu);
+        DeviceGuard guard(d->ordinal);
+        uint8_t* d_buf = nullptr;
+        MXD_CUDA(cudaMalloc(&d_buf, n * (sizeof(mxd_span) + 32)));
+        int rc = MXD_OK;
+        uint64_t total = 0; for (uint64_t i = 0; i < n; ++i) total += spans[i].len;
+        cudaError_t e = cudaMemcpyAsync(d_buf, spans, n * sizeof(mxd_span), cudaMemcpyHostToDevice, d->compute);
+        if (e == cudaSuccess) {
+            mxd::MsgJob j{};
+            j.spans = d_buf; j.nmsg = n; j.out = d_buf + n * sizeof(mxd_span); j.finalize = 1; j.one = 1;
+            e = mxd::launch_sha256(j, d->compute);
+            c->launches++; c->bytes_hashed += total;
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_buf + n * sizeof(mxd_span), n * 32, cudaMemcpyDeviceToHost, d->compute);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(d->compute);
+        if (e != cudaSuccess) rc = fail(MXD_ERR_CUDA, cudaGetErrorString(e));
+        c->d2h += n * 32;
+        cudaFree(d_buf);
+        return rc;
+    }
+    LockstepInput in;
+    in.src.resize(n); in.len.resize(n);
+    for (uint64_t i = 0; i < n; ++i) { in.src[i].mem = static_cast<const uint8_t*>(spans[i].ptr); in.len[i] = spans[i].len; }
+    return lockstep_digest(c, pick_device(c), in, out);
+}
+
+int mxd_sha256(mxd_ctx* c, const void* data, uint64_t n, uint8_t out[32]) {
+    if (!c || !out || (n && !data)) return fail(MXD_ERR_INVALID, "sha256: bad arguments");
+    mxd_span sp{data, n};
+    return mxd_sha256_batch(c, &sp, 1, out);
+}
+
+int mxd_sha256_files(mxd_ctx* c, const char* const* paths, uint64_t n, uint8_t* out, uint64_t* sizes) {
+    if (!c || (n && (!paths || !out))) return fail(MXD_ERR_INVALID, "sha256_files: bad arguments");
+    if (n == 0) return MXD_OK;
+    LockstepInput in; std::vector<int> fds;
+    int rc = open_files(paths, n, &in, &fds);
+    if (rc != MXD_OK) return rc;
+    if (sizes) for (uint64_t i = 0; i < n; ++i) sizes[i] = in.len[i];
+    rc = lockstep_digest(c, pick_device(c), in, out);
+    for (int fd : fds) close(fd);
+    return rc;
+}
+
+int mxd_sha256_file(mxd_ctx* c, const char* path, uint8_t out[32], uint64_t* size) {
+    if (!path) return fail(MXD_ERR_INVALID, "sha256_file: null path");
+    const char* paths[1] = {path};
+    return mxd_sha256_files(c, paths, 1, out, size);
+}
+
+int mxd_verify_batch(mxd_ctx* c, const mxd_span* spans, const uint8_t* want, uint64_t n, uint8_t* ok) {
+    if (!c || (n && (!spans || !want || !ok))) return fail(MXD_ERR_INVALID, "verify_batch: bad arguments");
+    std::vector<uint8_t> got(n * 32);
+    int rc = mxd_sha256_batch(c, spans, n, got.data());
+    if (rc != MXD_OK) return rc;
+    for (uint64_t i = 0; i < n; ++i) ok[i] = memcmp(&got[32 * i], want + 32 * i, 32) == 0;
+    return MXD_OK;
+}
+
+int mxd_verify_files(mxd_ctx* c, const char* const* paths, const uint8_t* want, uint64_t n, uint8_t* ok) {
+    if (!c || (n && (!paths || !want || !ok))) return fail(MXD_ERR_INVALID, "verify_files: bad arguments");
+    std::vector<uint8_t> got(n * 32);
+    int rc = mxd_sha256_files(c, paths, n, got.data(), nullptr);
+    if (rc != MXD_OK) return rc;
+    for (uint64_t i = 0; i < n; ++i) ok[i] = memcmp(&got[32 * i], want + 32 * i, 32) == 0;
+    return MXD_OK;
+}
+
+// ---- pinned memory -----------------------------------------------------------------------------------
+int mxd_host_alloc(mxd_ctx* c, void** out, uint64_t nbytes) {
+    if (!c || !out) return fail(MXD_ERR_INVALID, "host_alloc: bad arguments");
+    MXD_CUDA(cudaHostAlloc(out, nbytes, cudaHostAllocPortable));
+    return MXD_OK;
+}
+void mxd_host_free(mxd_ctx*, void* p) { if (p) cudaFreeHost(p); }
+int mxd_host_register(mxd_ctx* c, void* p, uint64_t nbytes) {
+    if (!c || !p) return fail(MXD_ERR_INVALID, "host_register: bad arguments");
+    MXD_CUDA(cudaHostRegister(p, nbytes, cudaHostRegisterPortable));
+    return MXD_OK;
+}
+int mxd_host_unregister(mxd_ctx* c, void* p) {
+    if (!c || !p) return fail(MXD_ERR_INVALID, "host_unregister: bad arguments");
+    MXD_CUDA(cudaHostUnregister(p));
+    return MXD_OK;
+}
+
+}  // extern "C"
+
+// ---- incremental hasher (hash.Hash shape, helper.go:46-49) --------------------------------------------
+// Writes accumulate in a pinned buffer; every full buffer advances the chain on the GPU (state
+// stays in device memory).  Sum hashes the unflushed tail with finalize on a scratch copy, so the
+// running state is untouched, as Go's Sum requires.
+struct mxd_hasher {
+    mxd_ctx* ctx = nullptr;
+    DevState* dev = nullptr;
+    uint8_t* h_buf = nullptr;  // pinned
+    uint8_t* d_buf = nullptr;
+    uint32_t* d_state = nullptr;
+    uint8_t* d_out = nullptr;
+    uint64_t cap = 0, fill = 0, absorbed = 0;
+    std::mutex mu;
+};
+
+namespace {
+constexpr uint64_t kHasherBuf = 4ull << 20;
+
+int hasher_launch(mxd_hasher* h, uint64_t nbytes, int finalize, uint32_t* state, uint8_t* d_out) {
+    mxd_ctx* c = h->ctx;
+    cudaStream_t st = h->dev->compute;
+    if (nbytes) MXD_CUDA(cudaMemcpyAsync(h->d_buf, h->h_buf, nbytes, cudaMemcpyHostToDevice, st));
+    mxd::MsgJob j{};
+    j.base = h->d_buf; j.nbytes = nbytes; j.seg = nbytes ? nbytes : 64; j.nmsg = 1;
+    j.out = d_out; j.state = state; j.prefix_all = h->absorbed; j.finalize = finalize; j.one = 1;
+    MXD_CUDA(mxd::launch_sha256(j, st));
+    c->launches++; c->bytes_hashed += nbytes; c->h2d += nbytes;
+    return MXD_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int mxd_hasher_new(mxd_ctx* c, mxd_hasher** out) {
+    if (!c || !out) return fail(MXD_ERR_INVALID, "hasher_new: bad arguments");
+    auto* h = new mxd_hasher();
+    h->ctx = c; h->dev = pick_device(c); h->cap = kHasherBuf;
+    DeviceGuard guard(h->dev->ordinal);
+    cudaError_t e = cudaHostAlloc(&h->h_buf, h->cap, cudaHostAllocPortable);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_buf, h->cap);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_state, 64);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_out, 32);
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_state, kIVHost, 32, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { int rc = fail(MXD_ERR_CUDA, std::string("hasher_new: ") + cudaGetErrorString(e)); mxd_hasher_free(h); return rc; }
+    *out = h;
+    return MXD_OK;
+}
+
+int mxd_hasher_write(mxd_hasher* h, const void* data, uint64_t n) {
+    if (!h || (n && !data)) return fail(MXD_ERR_INVALID, "hasher_write: bad arguments");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard guard(h->dev->ordinal);
+    const uint8_t* p = static_cast<const uint8_t*>(data);
+    while (n) {
+        const uint64_t take = std::min(n, h->cap - h->fill);
+        memcpy(h->h_buf + h->fill, p, take);
+        h->fill += take; p += take; n -= take;
+        if (h->fill == h->cap) {
+            std::lock_guard<std::mutex> dl(h->dev->mu);
+            int rc = hasher_launch(h, h->cap, 0, h->d_state, h->d_out);
+            if (rc != MXD_OK) return rc;
+            MXD_CUDA(cudaStreamSynchronize(h->dev->compute));  // h_buf is about to be overwritten
+            h->absorbed += h->cap; h->fill = 0;
+        }
+    }
+    return MXD_OK;
+}
+
+int mxd_hasher_sum(mxd_hasher* h, uint8_t out[32]) {
+    if (!h || !out) return fail(MXD_ERR_INVALID, "hasher_sum: bad arguments");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard guard(h->dev->ordinal);
+    std::lock_guard<std::mutex> dl(h->dev->mu);
+    // finalize reads the running state but does not write it back
+    int rc = hasher_launch(h, h->fill, 1, h->d_state, h->d_out);
+    if (rc != MXD_OK) return rc;
+    MXD_CUDA(cudaMemcpyAsync(out, h->d_out, 32, cudaMemcpyDeviceToHost, h->dev->compute));
+    MXD_CUDA(cudaStreamSynchronize(h->dev->compute));
+    h->ctx->d2h += 32;
+    return MXD_OK;
+}
+
+int mxd_hasher_reset(mxd_hasher* h) {
+    if (!h) return fail(MXD_ERR_INVALID, "hasher_reset: null");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard guard(h->dev->ordinal);
+    MXD_CUDA(cudaMemcpy(h->d_state, kIVHost, 32, cudaMemcpyHostToDevice));
+    h->fill = 0; h->absorbed = 0;
+    return MXD_OK;
+}
+
+uint64_t mxd_hasher_size(const mxd_hasher* h) { return h ? h->absorbed + h->fill : 0; }
+
+void mxd_hasher_free(mxd_hasher* h) {
+    if (!h) return;
+    if (h->dev) { DeviceGuard guard(h->dev->ordinal);
+        if (h->h_buf) cudaFreeHost(h->h_buf);
+        if (h->d_buf) cudaFree(h->d_buf);
+        if (h->d_state) cudaFree(h->d_state);
+        if (h->d_out) cudaFree(h->d_out);
+    }
+    delete h;
+}
+
+}  // extern "C"

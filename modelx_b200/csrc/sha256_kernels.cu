@@ -1,0 +1,244 @@
+// Multi-stream SHA-256 for sm_100a: one independent message per lane, a warp hashes 32
+// messages in lock step.  This is the kernel behind every digest modelx-b200 produces:
+//   - leaf / chunk / upper tree levels of a blob (uniform segments of one buffer),
+//   - batches of whole blobs (arbitrary spans; the reference's one-digest-per-file semantics,
+//     pkg/client/push.go:149-161 and pull.go:115-123, across many files at once),
+//   - chained segments of a single stream (hash.Hash-shaped incremental API, helper.go:46).
+// Pure 32-bit integer work: no tensor cores, no shared memory (the 16-word schedule and the
+// chain state live in registers; round constants are instruction immediates).
+#include "kernels.h"
+#include "sha256_device.cuh"
+#include <cstdlib>
+
+namespace mxd {
+
+namespace {
+
+constexpr int kThreads = 128;
+
+__device__ __forceinline__ uint4 ldg128(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+// 64 message bytes at p (any alignment) -> 16 big-endian words.
+// a = p & 3; q = p - a is 4-byte aligned.  Little-endian word k of the block is
+// funnelshift_r(q[k], q[k+1], 8a).  q[16] is only touched when a != 0, in which case it holds
+// the block's last byte(s), so it is inside the message.
+__device__ __forceinline__ void load_block_unaligned(const uint8_t* p, uint32_t (&w)[16]) {
+    const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3u);
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(p - a);
+    if (a == 0) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) w[k] = bswap32(__ldg(q + k));
+    } else {
+        uint32_t lo = __ldg(q);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            uint32_t hi = __ldg(q + k + 1);
+            w[k] = bswap32(__funnelshift_r(lo, hi, 8 * a));
+            lo = hi;
+        }
+    }
+}
+
+__device__ __forceinline__ void unpack_block(const uint4& v0, const uint4& v1, const uint4& v2, const uint4& v3,
+                                             uint32_t (&w)[16]) {
+    w[0] = bswap32(v0.x);  w[1] = bswap32(v0.y);  w[2] = bswap32(v0.z);  w[3] = bswap32(v0.w);
+    w[4] = bswap32(v1.x);  w[5] = bswap32(v1.y);  w[6] = bswap32(v1.z);  w[7] = bswap32(v1.w);
+    w[8] = bswap32(v2.x);  w[9] = bswap32(v2.y);  w[10] = bswap32(v2.z); w[11] = bswap32(v2.w);
+    w[12] = bswap32(v3.x); w[13] = bswap32(v3.y); w[14] = bswap32(v3.z); w[15] = bswap32(v3.w);
+}
+
+// MINB = resident CTAs per SM the register allocator must allow (8 -> 64 regs, 6 -> 80 regs).
+template <int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) k_sha256_lanes(const MsgJob j) {
+    const uint64_t m = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+    const bool valid = m < j.nmsg;
+    const uint32_t one = j.one;
+
+    // ---- locate this lane's message ------------------------------------------------------
+    const uint8_t* ptr = nullptr;
+    uint64_t len = 0;
+    if (valid) {
+        if (j.base != nullptr) {
+            const uint64_t off = m * j.seg;
+            ptr = j.base + off;
+            len = (off < j.nbytes) ? ((j.nbytes - off < j.seg) ? j.nbytes - off : j.seg) : 0;
+        } else {
+            const DevSpan sp = reinterpret_cast<const DevSpan*>(j.spans)[m];
+            ptr = static_cast<const uint8_t*>(sp.ptr);
+            len = sp.len;
+        }
+    }
+    uint32_t h[8];
+    if (valid && j.state != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) h[i] = j.state[8 * m + i];
+    } else {
+        sha256_iv(h);
+    }
+    const uint64_t prefix = (j.prefix != nullptr && valid) ? j.prefix[m] : j.prefix_all;
+    const uint64_t nfull = len >> 6;
+    const uint32_t r = (uint32_t)(len & 63u);
+    // blocks this lane compresses: the full ones, then (when finalizing) the padded tail block
+    // and, if the 64-bit length does not fit behind the tail, one more (FIPS 180-4 section 5.1.1).
+    int fin = j.finalize;
+    bool live = valid;
+    if (j.ctl != nullptr && valid) { const uint8_t c = j.ctl[m]; fin = (c == 1); live = (c != 2); }
+    const uint64_t nblk = live ? nfull + (fin ? (r >= 56 ? 2u : 1u) : 0u) : 0;
+    const uint64_t bits = (prefix + len) << 3;
+
+    // Fast path when every lane of the warp has a 16-byte aligned message (always true for tree
+    // levels): 4 x LDG.128 per block, next block prefetched into registers while this one is
+    // compressed.  Lane i streams its own message, so each request touches 32 different lines but
+    // consumes whole 32-byte sectors: DRAM traffic equals the algorithmic bytes.
+    const bool warp_aligned = __all_sync(0xffffffffu, (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0);
+    const uint4* p4 = reinterpret_cast<const uint4*>(ptr);
+    uint4 v0, v1, v2, v3;
+    if (warp_aligned && nfull) { v0 = ldg128(p4); v1 = ldg128(p4 + 1); v2 = ldg128(p4 + 2); v3 = ldg128(p4 + 3); }
+
+    uint32_t w[16];
+    for (uint64_t b = 0; b < nblk; ++b) {
+        if (b < nfull) {
+            if (warp_aligned) {
+                unpack_block(v0, v1, v2, v3, w);
+                if (b + 1 < nfull) {
+                    p4 += 4;
+                    v0 = ldg128(p4); v1 = ldg128(p4 + 1); v2 = ldg128(p4 + 2); v3 = ldg128(p4 + 3);
+                }
+            } else {
+                load_block_unaligned(ptr + (b << 6), w);
+            }
+        } else if (b == nfull) {
+            // r tail bytes, the 0x80 marker, zeros; the length too when it fits (r < 56)
+            const uint8_t* t = ptr + (nfull << 6);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                uint32_t word = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t idx = 4 * k + q;
+                    if (idx < r) word |= (uint32_t)__ldg(t + idx) << (24 - 8 * q);
+                    else if (idx == r) word |= 0x80u << (24 - 8 * q);
+                }
+                w[k] = word;
+            }
+            if (r < 56) { w[14] = (uint32_t)(bits >> 32); w[15] = (uint32_t)bits; }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 14; ++k) w[k] = 0;
+            w[14] = (uint32_t)(bits >> 32); w[15] = (uint32_t)bits;
+        }
+        sha256_compress(h, w, one);
+    }
+
+    if (!live) return;
+    if (!fin) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) j.state[8 * m + i] = h[i];
+        return;
+    }
+    uint4 lo, hi;
+    lo.x = bswap32(h[0]); lo.y = bswap32(h[1]); lo.z = bswap32(h[2]); lo.w = bswap32(h[3]);
+    hi.x = bswap32(h[4]); hi.y = bswap32(h[5]); hi.z = bswap32(h[6]); hi.w = bswap32(h[7]);
+    uint4* o = reinterpret_cast<uint4*>(j.out + 32 * m);
+    o[0] = lo; o[1] = hi;
+}
+
+// One thread: the 72-byte root message of modelx.tree.v1 (two blocks with padding).
+__global__ void k_tree_root(uint64_t size, uint64_t leaf, uint32_t fanout, const uint8_t* __restrict__ top,
+                            uint8_t* __restrict__ root, uint32_t one) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    uint8_t msg[128];
+    const char magic[16] = {'m', 'o', 'd', 'e', 'l', 'x', '.', 't', 'r', 'e', 'e', '.', 'v', '1', 0, 0};
+    for (int i = 0; i < 16; ++i) msg[i] = (uint8_t)magic[i];
+    for (int i = 0; i < 8; ++i) { msg[16 + i] = (uint8_t)(size >> (8 * i)); msg[24 + i] = (uint8_t)(leaf >> (8 * i)); }
+    for (int i = 0; i < 4; ++i) { msg[32 + i] = (uint8_t)(fanout >> (8 * i)); msg[36 + i] = 0; }
+    for (int i = 0; i < 32; ++i) msg[40 + i] = top[i];
+    msg[72] = 0x80;
+    for (int i = 73; i < 128; ++i) msg[i] = 0;
+    msg[126] = (uint8_t)((72 * 8) >> 8); msg[127] = (uint8_t)(72 * 8);
+    uint32_t h[8]; sha256_iv(h);
+    uint32_t w[16];
+    for (int b = 0; b < 2; ++b) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const uint8_t* q = msg + 64 * b + 4 * k;
+            w[k] = ((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | (uint32_t)q[3];
+        }
+        sha256_compress(h, w, one);
+    }
+    for (int i = 0; i < 8; ++i) {
+        root[4 * i] = (uint8_t)(h[i] >> 24); root[4 * i + 1] = (uint8_t)(h[i] >> 16);
+        root[4 * i + 2] = (uint8_t)(h[i] >> 8); root[4 * i + 3] = (uint8_t)h[i];
+    }
+}
+
+__global__ void k_compare(const uint8_t* __restrict__ got, const uint8_t* __restrict__ want, uint64_t n,
+                          uint8_t* __restrict__ ok) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t diff = 0;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) diff |= (uint32_t)(got[32 * i + k] ^ want[32 * i + k]);
+    ok[i] = diff == 0;
+}
+
+__device__ __forceinline__ uint64_t splitmix64_at(uint64_t seed, uint64_t jdx) {
+    uint64_t z = seed + (jdx + 1) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+__global__ void k_gen_fill(uint64_t* __restrict__ dst, uint64_t first_word, uint64_t nwords, uint64_t seed) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += stride)
+        dst[i] = splitmix64_at(seed, first_word + i);
+}
+
+}  // namespace
+
+// Occupancy variant (tuning knob, MXD_TUNE_MINB=6|8): 8 CTAs x 128 threads at <= 64 registers, or 6 at <= 80.
+static int g_minb = [] { const char* e = getenv("MXD_TUNE_MINB"); return (e && atoi(e) == 6) ? 6 : 8; }();
+
+cudaError_t launch_sha256(const MsgJob& job, cudaStream_t stream) {
+    if (job.nmsg == 0) return cudaSuccess;
+    const uint64_t blocks = (job.nmsg + kThreads - 1) / kThreads;
+    if (blocks > 0x7fffffffull) return cudaErrorInvalidValue;
+    if (g_minb == 6) k_sha256_lanes<6><<<(unsigned)blocks, kThreads, 0, stream>>>(job);
+    else             k_sha256_lanes<8><<<(unsigned)blocks, kThreads, 0, stream>>>(job);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_compare(const uint8_t* got, const uint8_t* want, uint64_t n, uint8_t* ok, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    k_compare<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(got, want, n, ok);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gen_fill(void* dst, uint64_t offset, uint64_t n, uint64_t seed, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    if ((offset | n) & 7u || (reinterpret_cast<uintptr_t>(dst) & 7u)) return cudaErrorInvalidValue;
+    const uint64_t nwords = n >> 3;
+    uint64_t blocks = (nwords + 255) / 256;
+    if (blocks > 148ull * 64) blocks = 148ull * 64;
+    k_gen_fill<<<(unsigned)blocks, 256, 0, stream>>>(static_cast<uint64_t*>(dst), offset >> 3, nwords, seed);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_tree_root(uint64_t size, uint64_t leaf, uint32_t fanout, const uint8_t* top, uint8_t* root,
+                             cudaStream_t stream) {
+    k_tree_root<<<1, 32, 0, stream>>>(size, leaf, fanout, top, root, 1u);
+    return cudaGetLastError();
+}
+
+int sha256_kernel_regs() {
+    cudaFuncAttributes a;
+    if (cudaFuncGetAttributes(&a, g_minb == 6 ? k_sha256_lanes<6> : k_sha256_lanes<8>) != cudaSuccess) return -1;
+    return a.numRegs;
+}
+
+}  // namespace mxd

@@ -1,0 +1,310 @@
+"""Thin object wrapper over the C ABI: one ``Engine`` = one ``mxd_ctx``.
+
+Everything here forwards to libmodelxdigest.so; no hashing happens in Python.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+from . import _native as N
+
+DEFAULT_CHUNK = 8 << 20   # bytes covered by one chunk digest (the list a manifest carries)
+DEFAULT_LEAF = 16 << 10   # bytes hashed by one GPU lane at the bottom of the tree
+
+
+def _buf(data):
+    """(address, nbytes, keepalive) of a bytes-like / numpy array without copying when possible."""
+    if isinstance(data, (bytes, bytearray)):
+        n = len(data)
+        if isinstance(data, bytes):
+            keep = C.create_string_buffer(data, n) if n else C.create_string_buffer(1)
+        else:
+            keep = (C.c_char * max(n, 1)).from_buffer(data)
+        return C.addressof(keep), n, keep
+    mv = memoryview(data)
+    if not mv.contiguous:
+        raise ValueError("buffer must be contiguous")
+    n = mv.nbytes
+    if hasattr(data, "ctypes"):  # numpy
+        return data.ctypes.data, n, data
+    keep = (C.c_char * max(n, 1)).from_buffer(mv) if not mv.readonly else C.create_string_buffer(mv.tobytes(), max(n, 1))
+    return C.addressof(keep), n, keep
+
+
+def digest_string(d: bytes) -> str:
+    """go-digest string form: ``sha256:<hex>`` (what Descriptor.Digest carries, pkg/types/types.go:31)."""
+    out = C.create_string_buffer(72)
+    N.load().mxd_digest_string((C.c_uint8 * 32).from_buffer_copy(d), out)
+    return out.value.decode()
+
+
+def digest_parse(s: str) -> bytes:
+    out = (C.c_uint8 * 32)()
+    N.check(N.load().mxd_digest_parse(s.encode(), out), "mxd_digest_parse")
+    return bytes(out)
+
+
+def calc_parts(total: int, partscount: int) -> List[Tuple[int, int]]:
+    """calcParts (pkg/client/extension_s3.go:99-112): [(offset, length)] for each part."""
+    lib = N.load()
+    if partscount > 0:
+        parts = (N.Part * partscount)()
+    else:
+        parts = (N.Part * 1)()
+    rc = lib.mxd_calc_parts(total, partscount, parts)
+    if rc == N.MXD_ERR_DIV_ZERO:
+        raise ZeroDivisionError("calcParts: integer divide by zero")   # the reference panics here
+    N.check(rc, "mxd_calc_parts")
+    return [(p.offset, p.length) for p in parts[:partscount]]
+
+
+def server_part_count(size: int, force_multipart: bool = False) -> int:
+    """Part count the modelxd S3 store chooses (pkg/registry/store_s3.go:198-203, 273-279)."""
+    return int(N.load().mxd_server_part_count(size, 1 if force_multipart else 0))
+
+
+def tree_shape(size: int, chunk: int = DEFAULT_CHUNK, leaf: int = DEFAULT_LEAF) -> List[int]:
+    counts = (C.c_uint64 * 64)()
+    lv = N.load().mxd_tree_shape(size, chunk, leaf, counts, 64)
+    if lv < 0:
+        raise N.MxdError(lv, "mxd_tree_shape")
+    return [int(counts[i]) for i in range(lv)]
+
+
+class Engine:
+    """One process-wide digest engine bound to one or more GPUs."""
+
+    def __init__(self, devices: Optional[Sequence[int]] = None, ring_bytes: int = 0):
+        self._lib = N.load()
+        self._ctx = C.c_void_p()
+        devs = list(devices) if devices is not None else []
+        arr = (C.c_int * max(len(devs), 1))(*devs)
+        N.check(self._lib.mxd_open(C.byref(self._ctx), arr if devs else None, len(devs), ring_bytes), "mxd_open")
+
+    # -- lifecycle ---------------------------------------------------------------------------
+    def close(self):
+        if self._ctx:
+            self._lib.mxd_close(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._ctx
+
+    def device_count(self) -> int:
+        return self._lib.mxd_device_count(self._ctx)
+
+    def stats(self) -> dict:
+        st = N.Stats()
+        N.check(self._lib.mxd_get_stats(self._ctx, C.byref(st)), "mxd_get_stats")
+        return {"kernel_launches": st.kernel_launches, "bytes_hashed": st.bytes_hashed,
+                "h2d_bytes": st.h2d_bytes, "d2h_bytes": st.d2h_bytes}
+
+    def cancel(self):
+        self._lib.mxd_cancel(self._ctx)
+
+    def reset_cancel(self):
+        self._lib.mxd_reset_cancel(self._ctx)
+
+    # -- whole-message digests (reference semantics) --------------------------------------------
+    def sha256(self, data) -> bytes:
+        addr, n, keep = _buf(data)
+        out = (C.c_uint8 * 32)()
+        N.check(self._lib.mxd_sha256(self._ctx, addr, n, out), "mxd_sha256")
+        return bytes(out)
+
+    def sha256_ptr(self, ptr: int, n: int) -> bytes:
+        out = (C.c_uint8 * 32)()
+        N.check(self._lib.mxd_sha256(self._ctx, ptr, n, out), "mxd_sha256")
+        return bytes(out)
+
+    def sha256_batch(self, items: Iterable) -> List[bytes]:
+        bufs = [_buf(x) for x in items]
+        n = len(bufs)
+        spans = (N.Span * max(n, 1))()
+        for i, (addr, ln, _) in enumerate(bufs):
+            spans[i].ptr = addr
+            spans[i].len = ln
+        out = (C.c_uint8 * (32 * max(n, 1)))()
+        N.check(self._lib.mxd_sha256_batch(self._ctx, spans, n, out), "mxd_sha256_batch")
+        raw = bytes(out)
+        return [raw[32 * i:32 * i + 32] for i in range(n)]
+
+    def sha256_batch_ptrs(self, spans_list: Sequence[Tuple[int, int]]) -> List[bytes]:
+        n = len(spans_list)
+        spans = (N.Span * max(n, 1))()
+        for i, (addr, ln) in enumerate(spans_list):
+            spans[i].ptr = addr
+            spans[i].len = ln
+        out = (C.c_uint8 * (32 * max(n, 1)))()
+        N.check(self._lib.mxd_sha256_batch(self._ctx, spans, n, out), "mxd_sha256_batch")
+        raw = bytes(out)
+        return [raw[32 * i:32 * i + 32] for i in range(n)]
+
+    def sha256_file(self, path: str) -> Tuple[bytes, int]:
+        out = (C.c_uint8 * 32)()
+        size = C.c_uint64()
+        N.check(self._lib.mxd_sha256_file(self._ctx, path.encode(), out, C.byref(size)), "mxd_sha256_file")
+        return bytes(out), size.value
+
+    def sha256_files(self, paths: Sequence[str]) -> Tuple[List[bytes], List[int]]:
+        n = len(paths)
+        arr = (C.c_char_p * max(n, 1))(*[p.encode() for p in paths])
+        out = (C.c_uint8 * (32 * max(n, 1)))()
+        sizes = (C.c_uint64 * max(n, 1))()
+        N.check(self._lib.mxd_sha256_files(self._ctx, arr, n, out, sizes), "mxd_sha256_files")
+        raw = bytes(out)
+        return [raw[32 * i:32 * i + 32] for i in range(n)], [int(sizes[i]) for i in range(n)]
+
+    def verify_batch(self, items: Iterable, want: Sequence[bytes]) -> List[bool]:
+        bufs = [_buf(x) for x in items]
+        n = len(bufs)
+        spans = (N.Span * max(n, 1))()
+        for i, (addr, ln, _) in enumerate(bufs):
+            spans[i].ptr = addr
+            spans[i].len = ln
+        w = (C.c_uint8 * (32 * max(n, 1))).from_buffer_copy(b"".join(want) + b"\0" * (32 * max(n, 1) - 32 * n))
+        ok = (C.c_uint8 * max(n, 1))()
+        N.check(self._lib.mxd_verify_batch(self._ctx, spans, w, n, ok), "mxd_verify_batch")
+        return [bool(ok[i]) for i in range(n)]
+
+    def verify_files(self, paths: Sequence[str], want: Sequence[bytes]) -> List[bool]:
+        n = len(paths)
+        arr = (C.c_char_p * max(n, 1))(*[p.encode() for p in paths])
+        w = (C.c_uint8 * (32 * max(n, 1))).from_buffer_copy(b"".join(want) + b"\0" * (32 * max(n, 1) - 32 * n))
+        ok = (C.c_uint8 * max(n, 1))()
+        N.check(self._lib.mxd_verify_files(self._ctx, arr, w, n, ok), "mxd_verify_files")
+        return [bool(ok[i]) for i in range(n)]
+
+    # -- incremental hasher ------------------------------------------------------------------
+    def hasher(self) -> "Hasher":
+        return Hasher(self)
+
+    # -- tree digests ------------------------------------------------------------------------
+    def tree_digest(self, data, chunk: int = DEFAULT_CHUNK, leaf: int = DEFAULT_LEAF):
+        """-> (chunk_digests: list[bytes], root: bytes) for a bytes-like blob in host memory."""
+        addr, n, keep = _buf(data)
+        return self.tree_digest_ptr(addr, n, chunk, leaf)
+
+    def tree_digest_ptr(self, ptr: int, n: int, chunk: int = DEFAULT_CHUNK, leaf: int = DEFAULT_LEAF):
+        nch = max(1, -(-n // chunk))
+        chunks = (C.c_uint8 * (32 * nch))()
+        got = C.c_uint64()
+        root = (C.c_uint8 * 32)()
+        N.check(self._lib.mxd_tree_digest(self._ctx, ptr, n, chunk, leaf, chunks, C.byref(got), root), "mxd_tree_digest")
+        raw = bytes(chunks)
+        return [raw[32 * i:32 * i + 32] for i in range(got.value)], bytes(root)
+
+    def tree_digest_file(self, path: str, chunk: int = DEFAULT_CHUNK, leaf: int = DEFAULT_LEAF):
+        import os
+        size = os.stat(path).st_size
+        nch = max(1, -(-size // chunk))
+        chunks = (C.c_uint8 * (32 * nch))()
+        got = C.c_uint64()
+        sz = C.c_uint64()
+        root = (C.c_uint8 * 32)()
+        N.check(self._lib.mxd_tree_digest_file(self._ctx, path.encode(), chunk, leaf, chunks, nch, C.byref(got),
+                                               C.byref(sz), root), "mxd_tree_digest_file")
+        raw = bytes(chunks)
+        return [raw[32 * i:32 * i + 32] for i in range(got.value)], bytes(root), sz.value
+
+    def tree_chunks_ptr(self, ptr: int, n: int, chunk: int = DEFAULT_CHUNK, leaf: int = DEFAULT_LEAF) -> bytes:
+        nch = max(1, -(-n // chunk))
+        chunks = (C.c_uint8 * (32 * nch))()
+        N.check(self._lib.mxd_tree_chunks(self._ctx, ptr, n, chunk, leaf, chunks), "mxd_tree_chunks")
+        return bytes(chunks)
+
+    def tree_chunks(self, data, chunk: int = DEFAULT_CHUNK, leaf: int = DEFAULT_LEAF) -> bytes:
+        addr, n, keep = _buf(data)
+        return self.tree_chunks_ptr(addr, n, chunk, leaf)
+
+    def tree_finish(self, chunk_digests: bytes, size: int, chunk: int = DEFAULT_CHUNK, leaf: int = DEFAULT_LEAF) -> bytes:
+        n = len(chunk_digests) // 32
+        arr = (C.c_uint8 * len(chunk_digests)).from_buffer_copy(chunk_digests)
+        root = (C.c_uint8 * 32)()
+        N.check(self._lib.mxd_tree_finish(self._ctx, arr, n, size, chunk, leaf, root), "mxd_tree_finish")
+        return bytes(root)
+
+    # -- device-resident asynchronous forms (raw device pointers, cudaStream_t as int) -----------
+    def dev_sha256_segments(self, dev: int, d_data: int, nbytes: int, seg: int, d_out: int, stream: int = 0):
+        N.check(self._lib.mxd_dev_sha256_segments(self._ctx, dev, d_data, nbytes, seg, d_out, stream), "mxd_dev_sha256_segments")
+
+    def dev_sha256_batch(self, dev: int, d_spans: int, n: int, d_out: int, stream: int = 0):
+        N.check(self._lib.mxd_dev_sha256_batch(self._ctx, dev, d_spans, n, d_out, stream), "mxd_dev_sha256_batch")
+
+    def dev_tree_chunks(self, dev: int, d_piece: int, nbytes: int, chunk: int, leaf: int, d_chunks: int, stream: int = 0):
+        N.check(self._lib.mxd_dev_tree_chunks(self._ctx, dev, d_piece, nbytes, chunk, leaf, d_chunks, stream), "mxd_dev_tree_chunks")
+
+    def dev_tree_finish(self, dev: int, d_chunks: int, nchunks: int, size: int, chunk: int, leaf: int, d_root: int, stream: int = 0):
+        N.check(self._lib.mxd_dev_tree_finish(self._ctx, dev, d_chunks, nchunks, size, chunk, leaf, d_root, stream), "mxd_dev_tree_finish")
+
+    def dev_tree_digest(self, dev: int, d_data: int, size: int, chunk: int, leaf: int, d_chunks: int, d_root: int, stream: int = 0):
+        N.check(self._lib.mxd_dev_tree_digest(self._ctx, dev, d_data, size, chunk, leaf, d_chunks, d_root, stream), "mxd_dev_tree_digest")
+
+    def dev_compare(self, dev: int, d_got: int, d_want: int, n: int, d_ok: int, stream: int = 0):
+        N.check(self._lib.mxd_dev_compare(self._ctx, dev, d_got, d_want, n, d_ok, stream), "mxd_dev_compare")
+
+    def dev_gen_fill(self, dev: int, d_dst: int, offset: int, n: int, seed: int, stream: int = 0):
+        N.check(self._lib.mxd_dev_gen_fill(self._ctx, dev, d_dst, offset, n, seed, stream), "mxd_dev_gen_fill")
+
+    # -- pinned memory -----------------------------------------------------------------------
+    def host_alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        N.check(self._lib.mxd_host_alloc(self._ctx, C.byref(p), nbytes), "mxd_host_alloc")
+        return p.value
+
+    def host_free(self, ptr: int):
+        self._lib.mxd_host_free(self._ctx, ptr)
+
+
+class Hasher:
+    """hash.Hash-shaped incremental SHA-256 (pkg/client/helper.go:46-49) running on the GPU."""
+
+    def __init__(self, engine: Engine):
+        self._e = engine
+        self._h = C.c_void_p()
+        N.check(engine._lib.mxd_hasher_new(engine._ctx, C.byref(self._h)), "mxd_hasher_new")
+
+    def write(self, data) -> int:
+        addr, n, keep = _buf(data)
+        N.check(self._e._lib.mxd_hasher_write(self._h, addr, n), "mxd_hasher_write")
+        return n
+
+    update = write
+
+    def sum(self) -> bytes:
+        out = (C.c_uint8 * 32)()
+        N.check(self._e._lib.mxd_hasher_sum(self._h, out), "mxd_hasher_sum")
+        return bytes(out)
+
+    digest = sum
+
+    def reset(self):
+        N.check(self._e._lib.mxd_hasher_reset(self._h), "mxd_hasher_reset")
+
+    def size(self) -> int:
+        return int(self._e._lib.mxd_hasher_size(self._h))
+
+    def close(self):
+        if self._h:
+            self._e._lib.mxd_hasher_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
