@@ -63,6 +63,11 @@ int  mxd_device_count(const mxd_ctx* ctx);
 void mxd_cancel(mxd_ctx* ctx);              /* abort in-flight streaming calls with MXD_ERR_CANCELED */
 void mxd_reset_cancel(mxd_ctx* ctx);
 int  mxd_get_stats(const mxd_ctx* ctx, mxd_stats* out);
+/* Live kernel timing for benchmarks: while enabled, every leaf-level SHA-256 launch (the launch
+ * that reads blob bytes) is bracketed by CUDA events on its own stream.  mxd_prof_read waits for
+ * them and returns the accumulated device time, launch count and message bytes, then clears. */
+int  mxd_prof_enable(mxd_ctx* ctx, int on);
+int  mxd_prof_read(mxd_ctx* ctx, double* kernel_ms, uint64_t* launches, uint64_t* bytes);
 const char* mxd_strerror(int status);
 const char* mxd_last_error(void);           /* thread-local detail of the last failure on this thread */
 int  mxd_abi_version(void);
@@ -90,24 +95,35 @@ uint64_t mxd_hasher_size(const mxd_hasher*);   /* bytes written so far */
 void mxd_hasher_free(mxd_hasher*);
 
 /* ---- chunked tree digest (new; what lets one blob use every lane and every GPU) -----------
- * "modelx.tree.v1": leaf i = SHA-256 of bytes [i*leaf, (i+1)*leaf); every following level hashes
- * groups of `fanout = chunk/leaf` consecutive digests; level 1 are the chunk digests (one per
- * `chunk` bytes, the list a manifest carries); levels repeat until one digest (top) is left;
- * root = SHA-256("modelx.tree.v1\0\0" || LE64(size) || LE64(leaf) || LE32(fanout) || LE32(0) || top).
- * Every node is a plain SHA-256 of well-defined bytes (bit-exact vs crypto/sha256 on them).
- * The root is NOT the reference's whole-file digest; see DESIGN.md.
- * chunk must be a multiple of leaf, leaf a multiple of 64, chunk/leaf >= 2. */
-int mxd_tree_shape(uint64_t size, uint64_t chunk, uint64_t leaf, uint64_t* counts, int max_levels); /* returns #levels */
-int mxd_tree_digest(mxd_ctx*, const void* data /*host or device*/, uint64_t size, uint64_t chunk, uint64_t leaf,
+ * "modelx.tree.v1" with parameters (leaf, fanout, chunk = leaf * fanout^k, k >= 1):
+ *   level 0:  leaf i = SHA-256 of bytes [i*leaf, (i+1)*leaf)   (n0 = max(1, ceil(size/leaf)) leaves)
+ *   level j+1: node i = SHA-256 of the concatenated level-j digests [i*fanout, (i+1)*fanout)
+ *   levels are built at least up to level k -- whose nodes each cover `chunk` bytes: these are the
+ *   CHUNK DIGESTS, the list a manifest carries -- and further while a level has more than one node;
+ *   top = the single digest of the last level;
+ *   root = SHA-256("modelx.tree.v1\0\0" || LE64(size) || LE64(leaf) || LE32(fanout) || LE32(0) || top).
+ * Every node is a plain SHA-256 of well-defined bytes (bit-exact vs crypto/sha256 on those bytes).
+ * The root is NOT the reference's whole-file digest (push.go:160); see DESIGN.md section 3.
+ * A NULL params pointer means the defaults: chunk 8 MiB, leaf 16 KiB, fanout 8. */
+typedef struct {
+    uint64_t chunk;     /* bytes per chunk digest; leaf * fanout^k */
+    uint64_t leaf;      /* bytes hashed by one GPU lane; multiple of 64 */
+    uint32_t fanout;    /* digests per upper-level node; >= 2 */
+    uint32_t reserved;  /* 0 */
+} mxd_tree_params;
+
+int mxd_tree_shape(uint64_t size, const mxd_tree_params* tp, uint64_t* counts, int max_levels,
+                   int* chunk_level); /* returns #levels */
+int mxd_tree_digest(mxd_ctx*, const void* data /*host or device*/, uint64_t size, const mxd_tree_params* tp,
                     uint8_t* chunk_digests /*nchunks*32, may be NULL*/, uint64_t* nchunks, uint8_t root[32]);
-int mxd_tree_digest_file(mxd_ctx*, const char* path, uint64_t chunk, uint64_t leaf,
+int mxd_tree_digest_file(mxd_ctx*, const char* path, const mxd_tree_params* tp,
                          uint8_t* chunk_digests, uint64_t cap_chunks, uint64_t* nchunks, uint64_t* size, uint8_t root[32]);
 /* Sharded form (one process per GPU): chunk digests of a piece that starts on a chunk boundary... */
-int mxd_tree_chunks(mxd_ctx*, const void* piece /*host or device*/, uint64_t nbytes, uint64_t chunk, uint64_t leaf,
-                    uint8_t* chunk_digests /*ceil(nbytes/chunk)*32 (>=1)*/);
+int mxd_tree_chunks(mxd_ctx*, const void* piece /*host or device*/, uint64_t nbytes, const mxd_tree_params* tp,
+                    uint8_t* chunk_digests /*max(1, ceil(nbytes/chunk))*32*/);
 /* ...and the levels above the gathered chunk list (the only step after the all-gather). */
-int mxd_tree_finish(mxd_ctx*, const uint8_t* chunk_digests, uint64_t nchunks, uint64_t size, uint64_t chunk,
-                    uint64_t leaf, uint8_t root[32]);
+int mxd_tree_finish(mxd_ctx*, const uint8_t* chunk_digests, uint64_t nchunks, uint64_t size,
+                    const mxd_tree_params* tp, uint8_t root[32]);
 
 /* ---- multipart split: integer-only, bit-exact with the reference ------------------------- */
 int     mxd_calc_parts(int64_t total, int64_t partscount, mxd_part* out /*partscount*/);   /* calcParts, extension_s3.go:99-112 */
@@ -131,11 +147,11 @@ int  mxd_host_unregister(mxd_ctx*, void* p);
 int mxd_dev_sha256_segments(mxd_ctx*, int dev, const void* d_data, uint64_t nbytes, uint64_t seg,
                             void* d_out /*ceil(nbytes/seg)*32*/, void* stream);
 int mxd_dev_sha256_batch(mxd_ctx*, int dev, const mxd_span* d_spans /*device array*/, uint64_t n, void* d_out, void* stream);
-int mxd_dev_tree_chunks(mxd_ctx*, int dev, const void* d_piece, uint64_t nbytes, uint64_t chunk, uint64_t leaf,
+int mxd_dev_tree_chunks(mxd_ctx*, int dev, const void* d_piece, uint64_t nbytes, const mxd_tree_params* tp,
                         void* d_chunk_digests, void* stream);
 int mxd_dev_tree_finish(mxd_ctx*, int dev, const void* d_chunk_digests, uint64_t nchunks, uint64_t size,
-                        uint64_t chunk, uint64_t leaf, void* d_root /*32*/, void* stream);
-int mxd_dev_tree_digest(mxd_ctx*, int dev, const void* d_data, uint64_t size, uint64_t chunk, uint64_t leaf,
+                        const mxd_tree_params* tp, void* d_root /*32*/, void* stream);
+int mxd_dev_tree_digest(mxd_ctx*, int dev, const void* d_data, uint64_t size, const mxd_tree_params* tp,
                         void* d_chunk_digests /*may be NULL*/, void* d_root /*32*/, void* stream);
 int mxd_dev_compare(mxd_ctx*, int dev, const void* d_got, const void* d_want, uint64_t n, void* d_ok /*n bytes*/, void* stream);
 /* deterministic synthetic blob (benchmarks/tests): LE64 word j = splitmix64(seed, j); offset, n multiples of 8 */

@@ -4,8 +4,8 @@ The product is the C-ABI shared library ``libmodelxdigest.so`` (hand-written sm_
 this package is its Python host-side mirror of ``pkg/client``'s digest path.
 """
 from ._native import LIB_PATH, MxdError, load  # noqa: F401
-from .engine import (DEFAULT_CHUNK, DEFAULT_LEAF, Engine, Hasher, calc_parts, digest_parse,  # noqa: F401
+from .engine import (DEFAULT_CHUNK, DEFAULT_FANOUT, DEFAULT_LEAF, Engine, Hasher, calc_parts, digest_parse,  # noqa: F401
                      digest_string, server_part_count, tree_shape)
 
 __all__ = ["Engine", "Hasher", "calc_parts", "server_part_count", "digest_string", "digest_parse", "tree_shape",
-           "DEFAULT_CHUNK", "DEFAULT_LEAF", "MxdError", "load", "LIB_PATH"]
+           "DEFAULT_CHUNK", "DEFAULT_LEAF", "DEFAULT_FANOUT", "MxdError", "load", "LIB_PATH"]

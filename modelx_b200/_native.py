@@ -30,6 +30,10 @@ class Part(C.Structure):
     _fields_ = [("offset", C.c_int64), ("length", C.c_int64)]
 
 
+class TreeParams(C.Structure):
+    _fields_ = [("chunk", C.c_uint64), ("leaf", C.c_uint64), ("fanout", C.c_uint32), ("reserved", C.c_uint32)]
+
+
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("bytes_hashed", C.c_uint64), ("h2d_bytes", C.c_uint64),
                 ("d2h_bytes", C.c_uint64), ("reserved", C.c_uint64 * 4)]
@@ -47,6 +51,8 @@ PROTOTYPES = {
     "mxd_cancel": (None, [vp]),
     "mxd_reset_cancel": (None, [vp]),
     "mxd_get_stats": (C.c_int, [vp, C.POINTER(Stats)]),
+    "mxd_prof_enable": (C.c_int, [vp, C.c_int]),
+    "mxd_prof_read": (C.c_int, [vp, C.POINTER(C.c_double), u64p, u64p]),
     "mxd_strerror": (C.c_char_p, [C.c_int]),
     "mxd_last_error": (C.c_char_p, []),
     "mxd_abi_version": (C.c_int, []),
@@ -62,11 +68,11 @@ PROTOTYPES = {
     "mxd_hasher_reset": (C.c_int, [vp]),
     "mxd_hasher_size": (C.c_uint64, [vp]),
     "mxd_hasher_free": (None, [vp]),
-    "mxd_tree_shape": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, u64p, C.c_int]),
-    "mxd_tree_digest": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, C.c_uint64, u8p, u64p, u8p]),
-    "mxd_tree_digest_file": (C.c_int, [vp, C.c_char_p, C.c_uint64, C.c_uint64, u8p, C.c_uint64, u64p, u64p, u8p]),
-    "mxd_tree_chunks": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, C.c_uint64, u8p]),
-    "mxd_tree_finish": (C.c_int, [vp, u8p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, u8p]),
+    "mxd_tree_shape": (C.c_int, [C.c_uint64, C.POINTER(TreeParams), u64p, C.c_int, C.POINTER(C.c_int)]),
+    "mxd_tree_digest": (C.c_int, [vp, vp, C.c_uint64, C.POINTER(TreeParams), u8p, u64p, u8p]),
+    "mxd_tree_digest_file": (C.c_int, [vp, C.c_char_p, C.POINTER(TreeParams), u8p, C.c_uint64, u64p, u64p, u8p]),
+    "mxd_tree_chunks": (C.c_int, [vp, vp, C.c_uint64, C.POINTER(TreeParams), u8p]),
+    "mxd_tree_finish": (C.c_int, [vp, u8p, C.c_uint64, C.c_uint64, C.POINTER(TreeParams), u8p]),
     "mxd_calc_parts": (C.c_int, [C.c_int64, C.c_int64, C.POINTER(Part)]),
     "mxd_server_part_count": (C.c_int64, [C.c_int64, C.c_int]),
     "mxd_digest_string": (None, [u8p, C.c_char_p]),
@@ -77,9 +83,9 @@ PROTOTYPES = {
     "mxd_host_unregister": (C.c_int, [vp, vp]),
     "mxd_dev_sha256_segments": (C.c_int, [vp, C.c_int, vp, C.c_uint64, C.c_uint64, vp, vp]),
     "mxd_dev_sha256_batch": (C.c_int, [vp, C.c_int, vp, C.c_uint64, vp, vp]),
-    "mxd_dev_tree_chunks": (C.c_int, [vp, C.c_int, vp, C.c_uint64, C.c_uint64, C.c_uint64, vp, vp]),
-    "mxd_dev_tree_finish": (C.c_int, [vp, C.c_int, vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, vp, vp]),
-    "mxd_dev_tree_digest": (C.c_int, [vp, C.c_int, vp, C.c_uint64, C.c_uint64, C.c_uint64, vp, vp, vp]),
+    "mxd_dev_tree_chunks": (C.c_int, [vp, C.c_int, vp, C.c_uint64, C.POINTER(TreeParams), vp, vp]),
+    "mxd_dev_tree_finish": (C.c_int, [vp, C.c_int, vp, C.c_uint64, C.c_uint64, C.POINTER(TreeParams), vp, vp]),
+    "mxd_dev_tree_digest": (C.c_int, [vp, C.c_int, vp, C.c_uint64, C.POINTER(TreeParams), vp, vp, vp]),
     "mxd_dev_compare": (C.c_int, [vp, C.c_int, vp, vp, C.c_uint64, vp, vp]),
     "mxd_dev_gen_fill": (C.c_int, [vp, C.c_int, vp, C.c_uint64, C.c_uint64, C.c_uint64, vp]),
 }

@@ -58,6 +58,11 @@ struct mxd_ctx {
     std::atomic<uint64_t> launches{0}, bytes_hashed{0}, h2d{0}, d2h{0};
     std::atomic<int> canceled{0};
     std::atomic<uint32_t> rr{0};  // round-robin device pick for single-device calls
+    // live timing of leaf-level launches (mxd_prof_*)
+    std::atomic<int> prof_on{0};
+    std::mutex prof_mu;
+    struct ProfRec { cudaEvent_t a, b; uint64_t bytes; int ordinal; };
+    std::vector<ProfRec> prof;
 };
 
 namespace {
@@ -68,12 +73,39 @@ struct DeviceGuard {
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
-bool tree_params_ok(uint64_t chunk, uint64_t leaf) {
-    return leaf >= 64 && (leaf % 64) == 0 && chunk >= 2 * leaf && (chunk % leaf) == 0 && chunk / leaf <= 0xffffffffull;
+// Resolved tree parameters: chunk = leaf * fanout^klevel.
+struct Tree {
+    uint64_t chunk = 8ull << 20, leaf = 16ull << 10, fanout = 8;
+    int klevel = 3;
+};
+
+bool tree_resolve(const mxd_tree_params* tp, Tree* t) {
+    if (tp) { t->chunk = tp->chunk; t->leaf = tp->leaf; t->fanout = tp->fanout; }
+    if (t->leaf < 64 || (t->leaf % 64) != 0 || t->fanout < 2 || t->chunk < t->leaf) return false;
+    if (tp && tp->reserved != 0) return false;
+    uint64_t span = t->leaf;
+    int k = 0;
+    while (span < t->chunk) {
+        if (span > t->chunk / t->fanout) return false;   // overflow / not a power
+        span *= t->fanout; ++k;
+    }
+    if (span != t->chunk || k < 1) return false;
+    t->klevel = k;
+    return true;
 }
 
 // ---- kernel enqueue helpers ------------------------------------------------------------------
-int enqueue_segments(mxd_ctx* c, const uint8_t* d_data, uint64_t nbytes, uint64_t seg, uint8_t* d_out, cudaStream_t st) {
+int enqueue_segments(mxd_ctx* c, const uint8_t* d_data, uint64_t nbytes, uint64_t seg, uint8_t* d_out, cudaStream_t st,
+                     bool leaf_level = false) {
+    mxd_ctx::ProfRec rec{};
+    const bool prof = leaf_level && c->prof_on.load();
+    if (prof) {
+        cudaGetDevice(&rec.ordinal);
+        MXD_CUDA(cudaEventCreate(&rec.a));
+        MXD_CUDA(cudaEventCreate(&rec.b));
+        rec.bytes = nbytes;
+        MXD_CUDA(cudaEventRecord(rec.a, st));
+    }
     mxd::MsgJob j{};
     j.base = d_data; j.nbytes = nbytes; j.seg = seg;
     j.nmsg = nbytes ? (nbytes + seg - 1) / seg : 1;
@@ -83,45 +115,74 @@ int enqueue_segments(mxd_ctx* c, const uint8_t* d_data, uint64_t nbytes, uint64_
     }
     MXD_CUDA(mxd::launch_sha256(j, st));
     c->launches++; c->bytes_hashed += nbytes;
+    if (prof) {
+        MXD_CUDA(cudaEventRecord(rec.b, st));
+        std::lock_guard<std::mutex> lk(c->prof_mu);
+        c->prof.push_back(rec);
+    }
     return MXD_OK;
 }
 
+// digests of one tree level -> the next: groups of `fanout` digests
+int enqueue_level(mxd_ctx* c, const uint8_t* d_in, uint64_t n, uint64_t fanout, uint8_t* d_out, cudaStream_t st) {
+    return enqueue_segments(c, d_in, n * 32, 32 * fanout, d_out, st);
+}
+
+// leaf digests (level 0, n0 of them in d_leaves, clobbered as scratch) -> chunk digests (level k)
+int enqueue_leaves_to_chunks(mxd_ctx* c, const Tree& t, uint8_t* d_leaves, uint64_t n0, uint8_t* d_chunks, cudaStream_t st) {
+    // ping-pong between the leaf buffer and one scratch buffer of the level-1 size
+    uint64_t n = n0;
+    const uint64_t n1 = (n0 + t.fanout - 1) / t.fanout;
+    uint8_t* scratch = nullptr;
+    if (t.klevel > 1) MXD_CUDA(cudaMallocAsync(&scratch, n1 * 32, st));
+    uint8_t* cur = d_leaves;
+    int rc = MXD_OK;
+    for (int lv = 1; lv <= t.klevel && rc == MXD_OK; ++lv) {
+        const uint64_t nn = (n + t.fanout - 1) / t.fanout;
+        uint8_t* dst = (lv == t.klevel) ? d_chunks : ((cur == d_leaves) ? scratch : d_leaves);
+        rc = enqueue_level(c, cur, n, t.fanout, dst, st);
+        cur = dst; n = nn;
+    }
+    if (scratch) cudaFreeAsync(scratch, st);
+    return rc;
+}
+
 // leaves -> chunk digests for one piece resident in device memory
-int enqueue_tree_chunks(mxd_ctx* c, const uint8_t* d_piece, uint64_t nbytes, uint64_t chunk, uint64_t leaf,
-                        uint8_t* d_chunks, cudaStream_t st) {
-    const uint64_t fanout = chunk / leaf;
-    const uint64_t n0 = nbytes ? (nbytes + leaf - 1) / leaf : 1;
+int enqueue_tree_chunks(mxd_ctx* c, const Tree& t, const uint8_t* d_piece, uint64_t nbytes, uint8_t* d_chunks, cudaStream_t st) {
+    const uint64_t n0 = nbytes ? (nbytes + t.leaf - 1) / t.leaf : 1;
     uint8_t* ws = nullptr;
     MXD_CUDA(cudaMallocAsync(&ws, n0 * 32, st));
-    int rc = enqueue_segments(c, d_piece, nbytes, leaf, ws, st);
-    if (rc == MXD_OK) rc = enqueue_segments(c, ws, n0 * 32, 32 * fanout, d_chunks, st);
+    int rc = enqueue_segments(c, d_piece, nbytes, t.leaf, ws, st, /*leaf_level=*/true);
+    if (rc == MXD_OK) rc = enqueue_leaves_to_chunks(c, t, ws, n0, d_chunks, st);
     cudaFreeAsync(ws, st);
     return rc;
 }
 
 // levels above the chunk list, then the root message
-int enqueue_tree_finish(mxd_ctx* c, const uint8_t* d_chunks, uint64_t nchunks, uint64_t size, uint64_t chunk,
-                        uint64_t leaf, uint8_t* d_root, cudaStream_t st) {
-    const uint64_t fanout = chunk / leaf;
+int enqueue_tree_finish(mxd_ctx* c, const Tree& t, const uint8_t* d_chunks, uint64_t nchunks, uint64_t size,
+                        uint8_t* d_root, cudaStream_t st) {
     const uint8_t* cur = d_chunks;
     uint64_t n = nchunks;
-    uint8_t* owned = nullptr;
-    int rc = MXD_OK;
+    uint8_t* bufs[2] = {nullptr, nullptr};
+    int rc = MXD_OK, which = 0;
+    if (n > 1) {
+        const uint64_t n1 = (n + t.fanout - 1) / t.fanout;
+        for (int i = 0; i < 2 && rc == MXD_OK; ++i) {
+            cudaError_t e = cudaMallocAsync(&bufs[i], n1 * 32, st);
+            if (e != cudaSuccess) rc = fail(MXD_ERR_CUDA, std::string("cudaMallocAsync: ") + cudaGetErrorString(e));
+        }
+    }
     while (n > 1 && rc == MXD_OK) {
-        const uint64_t nn = (n + fanout - 1) / fanout;
-        uint8_t* nxt = nullptr;
-        cudaError_t e = cudaMallocAsync(&nxt, nn * 32, st);
-        if (e != cudaSuccess) { rc = fail(MXD_ERR_CUDA, std::string("cudaMallocAsync: ") + cudaGetErrorString(e)); break; }
-        rc = enqueue_segments(c, cur, n * 32, 32 * fanout, nxt, st);
-        if (owned) cudaFreeAsync(owned, st);
-        owned = nxt; cur = nxt; n = nn;
+        rc = enqueue_level(c, cur, n, t.fanout, bufs[which], st);
+        cur = bufs[which]; which ^= 1;
+        n = (n + t.fanout - 1) / t.fanout;
     }
     if (rc == MXD_OK) {
-        cudaError_t e = mxd::launch_tree_root(size, leaf, (uint32_t)fanout, cur, d_root, st);
+        cudaError_t e = mxd::launch_tree_root(size, t.leaf, (uint32_t)t.fanout, cur, d_root, st);
         if (e != cudaSuccess) rc = fail(MXD_ERR_CUDA, std::string("launch_tree_root: ") + cudaGetErrorString(e));
         else c->launches++;
     }
-    if (owned) cudaFreeAsync(owned, st);
+    for (int i = 0; i < 2; ++i) if (bufs[i]) cudaFreeAsync(bufs[i], st);
     return rc;
 }
 
@@ -194,7 +255,7 @@ int stream_segments(mxd_ctx* c, DevState* d, const Source& src, uint64_t nbytes,
         MXD_CUDA(cudaMemcpyAsync(d_slot, from, n, cudaMemcpyHostToDevice, d->copy));
         MXD_CUDA(cudaEventRecord(d->ev_copied[s], d->copy));
         MXD_CUDA(cudaStreamWaitEvent(d->compute, d->ev_copied[s], 0));
-        rc = enqueue_segments(c, d_slot, n, seg, d_out + (off / seg) * 32, d->compute);
+        rc = enqueue_segments(c, d_slot, n, seg, d_out + (off / seg) * 32, d->compute, /*leaf_level=*/true);
         if (rc != MXD_OK) return rc;
         MXD_CUDA(cudaEventRecord(d->ev_done[s], d->compute));
         c->h2d += n;
@@ -204,20 +265,14 @@ int stream_segments(mxd_ctx* c, DevState* d, const Source& src, uint64_t nbytes,
 }
 
 // chunk digests of a host/file piece on one device; result left in device memory d_chunks
-int stream_tree_chunks(mxd_ctx* c, DevState* d, const Source& src, uint64_t nbytes, uint64_t chunk, uint64_t leaf,
-                       uint8_t* d_chunks) {
-    const uint64_t fanout = chunk / leaf;
-    const uint64_t n0 = nbytes ? (nbytes + leaf - 1) / leaf : 1;
+int stream_tree_chunks(mxd_ctx* c, DevState* d, const Tree& t, const Source& src, uint64_t nbytes, uint8_t* d_chunks) {
+    const uint64_t n0 = nbytes ? (nbytes + t.leaf - 1) / t.leaf : 1;
     uint8_t* d_leaves = nullptr;
     MXD_CUDA(cudaMalloc(&d_leaves, n0 * 32));
-    int rc = stream_segments(c, d, src, nbytes, leaf, d_leaves);
-    if (rc == MXD_OK) rc = enqueue_segments(c, d_leaves, n0 * 32, 32 * fanout, d_chunks, d->compute);
-    if (rc == MXD_OK) {
-        cudaError_t e = cudaStreamSynchronize(d->compute);
-        if (e != cudaSuccess) rc = fail(MXD_ERR_CUDA, std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e));
-    } else {
-        cudaStreamSynchronize(d->compute);
-    }
+    int rc = stream_segments(c, d, src, nbytes, t.leaf, d_leaves);
+    if (rc == MXD_OK) rc = enqueue_leaves_to_chunks(c, t, d_leaves, n0, d_chunks, d->compute);
+    cudaError_t e = cudaStreamSynchronize(d->compute);
+    if (rc == MXD_OK && e != cudaSuccess) rc = fail(MXD_ERR_CUDA, std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e));
     cudaFree(d_leaves);
     return rc;
 }
@@ -225,7 +280,8 @@ int stream_tree_chunks(mxd_ctx* c, DevState* d, const Source& src, uint64_t nbyt
 // Chunk digests of a host/file blob using every device of the context: device g takes the
 // contiguous chunk range [g*n/G, (g+1)*n/G) (sequential reads per device, no data-path
 // collective).  Results land in host memory `out` (nchunks*32).
-int host_tree_chunks_all(mxd_ctx* c, const Source& src, uint64_t nbytes, uint64_t chunk, uint64_t leaf, uint8_t* out) {
+int host_tree_chunks_all(mxd_ctx* c, const Tree& t, const Source& src, uint64_t nbytes, uint8_t* out) {
+    const uint64_t chunk = t.chunk;
     const uint64_t nchunks = nbytes ? (nbytes + chunk - 1) / chunk : 1;
     const int G = (int)std::min<uint64_t>(c->devs.size(), nchunks);
     std::vector<int> rcs(G, MXD_OK);
@@ -241,7 +297,7 @@ int host_tree_chunks_all(mxd_ctx* c, const Source& src, uint64_t nbytes, uint64_
         uint8_t* d_chunks = nullptr;
         cudaError_t e = cudaMalloc(&d_chunks, (c1 - c0) * 32);
         if (e != cudaSuccess) { rcs[g] = MXD_ERR_CUDA; errs[g] = cudaGetErrorString(e); return; }
-        int rc = stream_tree_chunks(c, d, piece, b1 - b0, chunk, leaf, d_chunks);
+        int rc = stream_tree_chunks(c, d, t, piece, b1 - b0, d_chunks);
         if (rc == MXD_OK) {
             e = cudaMemcpy(out + c0 * 32, d_chunks, (c1 - c0) * 32, cudaMemcpyDeviceToHost);
             if (e != cudaSuccess) { rc = MXD_ERR_CUDA; g_last_error = cudaGetErrorString(e); }
@@ -264,8 +320,8 @@ int host_tree_chunks_all(mxd_ctx* c, const Source& src, uint64_t nbytes, uint64_
 }
 
 // upper levels + root from a host-resident chunk list (tiny: 32 B per chunk)
-int host_tree_finish(mxd_ctx* c, DevState* d, const uint8_t* chunks, uint64_t nchunks, uint64_t size, uint64_t chunk,
-                     uint64_t leaf, uint8_t root[32]) {
+int host_tree_finish(mxd_ctx* c, DevState* d, const Tree& t, const uint8_t* chunks, uint64_t nchunks, uint64_t size,
+                     uint8_t root[32]) {
     std::lock_guard<std::mutex> lk(d->mu);
     DeviceGuard guard(d->ordinal);
     uint8_t* d_buf = nullptr;
@@ -273,7 +329,7 @@ int host_tree_finish(mxd_ctx* c, DevState* d, const uint8_t* chunks, uint64_t nc
     int rc = MXD_OK;
     cudaError_t e = cudaMemcpyAsync(d_buf, chunks, nchunks * 32, cudaMemcpyHostToDevice, d->compute);
     if (e != cudaSuccess) rc = fail(MXD_ERR_CUDA, cudaGetErrorString(e));
-    if (rc == MXD_OK) rc = enqueue_tree_finish(c, d_buf, nchunks, size, chunk, leaf, d_buf + nchunks * 32, d->compute);
+    if (rc == MXD_OK) rc = enqueue_tree_finish(c, t, d_buf, nchunks, size, d_buf + nchunks * 32, d->compute);
     if (rc == MXD_OK) {
         e = cudaMemcpyAsync(root, d_buf + nchunks * 32, 32, cudaMemcpyDeviceToHost, d->compute);
         if (e == cudaSuccess) e = cudaStreamSynchronize(d->compute);
@@ -311,7 +367,7 @@ int lockstep_digest(mxd_ctx* c, DevState* d, const LockstepInput& in, uint8_t* o
     const uint64_t rounds = std::max<uint64_t>(1, (maxlen + S - 1) / S);
 
     // per-round descriptors live in pinned memory, double-buffered per slot
-    const uint64_t desc_bytes = n * (sizeof(mxd::DevSpan) + sizeof(uint64_t) + 1);
+    const uint64_t desc_bytes = (n * (sizeof(mxd::DevSpan) + sizeof(uint64_t) + 1) + 255) & ~255ull;
     uint8_t *h_desc = nullptr, *d_desc = nullptr, *d_out = nullptr;
     uint32_t* d_state = nullptr;
     MXD_CUDA(cudaMallocHost(&h_desc, desc_bytes * kSlots));
@@ -427,6 +483,33 @@ const char* mxd_strerror(int status) {
 }
 
 const char* mxd_last_error(void) { return g_last_error.c_str(); }
+
+int mxd_prof_enable(mxd_ctx* c, int on) {
+    if (!c) return fail(MXD_ERR_INVALID, "prof_enable: null");
+    c->prof_on.store(on ? 1 : 0);
+    return MXD_OK;
+}
+
+int mxd_prof_read(mxd_ctx* c, double* kernel_ms, uint64_t* launches, uint64_t* bytes) {
+    if (!c) return fail(MXD_ERR_INVALID, "prof_read: null");
+    std::vector<mxd_ctx::ProfRec> recs;
+    { std::lock_guard<std::mutex> lk(c->prof_mu); recs.swap(c->prof); }
+    double ms = 0; uint64_t nb = 0;
+    int rc = MXD_OK;
+    for (auto& r : recs) {
+        DeviceGuard guard(r.ordinal);
+        float t = 0;
+        cudaError_t e = cudaEventSynchronize(r.b);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&t, r.a, r.b);
+        if (e != cudaSuccess) rc = fail(MXD_ERR_CUDA, std::string("prof_read: ") + cudaGetErrorString(e));
+        ms += t; nb += r.bytes;
+        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    if (kernel_ms) *kernel_ms = ms;
+    if (launches) *launches = recs.size();
+    if (bytes) *bytes = nb;
+    return rc;
+}
 
 int mxd_open(mxd_ctx** out, const int* devices, int ndev, uint64_t ring_bytes) {
     if (!out || ndev < 0 || (ndev > 0 && !devices)) return fail(MXD_ERR_INVALID, "mxd_open: bad arguments");
@@ -561,17 +644,18 @@ int mxd_digest_parse(const char* s, uint8_t out[32]) {
 }
 
 // ---- tree ---------------------------------------------------------------------------------------------
-int mxd_tree_shape(uint64_t size, uint64_t chunk, uint64_t leaf, uint64_t* counts, int max_levels) {
-    if (!tree_params_ok(chunk, leaf) || !counts || max_levels < 2) return fail(MXD_ERR_INVALID, "tree: bad chunk/leaf");
-    const uint64_t fanout = chunk / leaf;
-    uint64_t n = size ? (size + leaf - 1) / leaf : 1;
+int mxd_tree_shape(uint64_t size, const mxd_tree_params* tp, uint64_t* counts, int max_levels, int* chunk_level) {
+    Tree t;
+    if (!tree_resolve(tp, &t) || !counts || max_levels < 2) return fail(MXD_ERR_INVALID, "tree: chunk must be leaf * fanout^k (k >= 1), leaf a multiple of 64, fanout >= 2");
+    uint64_t n = size ? (size + t.leaf - 1) / t.leaf : 1;
     int lv = 0;
     counts[lv++] = n;
-    do {
+    while (lv <= t.klevel || n > 1) {
         if (lv >= max_levels) return fail(MXD_ERR_INVALID, "tree: too many levels for counts[]");
-        n = (n + fanout - 1) / fanout;
+        n = (n + t.fanout - 1) / t.fanout;
         counts[lv++] = n;
-    } while (n > 1);
+    }
+    if (chunk_level) *chunk_level = t.klevel;
     return lv;
 }
 
@@ -592,36 +676,39 @@ int mxd_dev_sha256_batch(mxd_ctx* c, int dev, const mxd_span* d_spans, uint64_t 
     return MXD_OK;
 }
 
-int mxd_dev_tree_chunks(mxd_ctx* c, int dev, const void* d_piece, uint64_t nbytes, uint64_t chunk, uint64_t leaf,
+int mxd_dev_tree_chunks(mxd_ctx* c, int dev, const void* d_piece, uint64_t nbytes, const mxd_tree_params* tp,
                         void* d_chunk_digests, void* stream) {
-    if (!c || dev < 0 || dev >= (int)c->devs.size() || !tree_params_ok(chunk, leaf) || !d_chunk_digests)
+    Tree t;
+    if (!c || dev < 0 || dev >= (int)c->devs.size() || !tree_resolve(tp, &t) || !d_chunk_digests)
         return fail(MXD_ERR_INVALID, "dev_tree_chunks: bad arguments");
     DeviceGuard guard(c->devs[dev]->ordinal);
-    return enqueue_tree_chunks(c, static_cast<const uint8_t*>(d_piece), nbytes, chunk, leaf,
-                               static_cast<uint8_t*>(d_chunk_digests), (cudaStream_t)stream);
+    return enqueue_tree_chunks(c, t, static_cast<const uint8_t*>(d_piece), nbytes, static_cast<uint8_t*>(d_chunk_digests),
+                               (cudaStream_t)stream);
 }
 
-int mxd_dev_tree_finish(mxd_ctx* c, int dev, const void* d_chunk_digests, uint64_t nchunks, uint64_t size, uint64_t chunk,
-                        uint64_t leaf, void* d_root, void* stream) {
-    if (!c || dev < 0 || dev >= (int)c->devs.size() || !tree_params_ok(chunk, leaf) || !d_chunk_digests || !d_root || nchunks == 0)
+int mxd_dev_tree_finish(mxd_ctx* c, int dev, const void* d_chunk_digests, uint64_t nchunks, uint64_t size,
+                        const mxd_tree_params* tp, void* d_root, void* stream) {
+    Tree t;
+    if (!c || dev < 0 || dev >= (int)c->devs.size() || !tree_resolve(tp, &t) || !d_chunk_digests || !d_root || nchunks == 0)
         return fail(MXD_ERR_INVALID, "dev_tree_finish: bad arguments");
     DeviceGuard guard(c->devs[dev]->ordinal);
-    return enqueue_tree_finish(c, static_cast<const uint8_t*>(d_chunk_digests), nchunks, size, chunk, leaf,
+    return enqueue_tree_finish(c, t, static_cast<const uint8_t*>(d_chunk_digests), nchunks, size,
                                static_cast<uint8_t*>(d_root), (cudaStream_t)stream);
 }
 
-int mxd_dev_tree_digest(mxd_ctx* c, int dev, const void* d_data, uint64_t size, uint64_t chunk, uint64_t leaf,
+int mxd_dev_tree_digest(mxd_ctx* c, int dev, const void* d_data, uint64_t size, const mxd_tree_params* tp,
                         void* d_chunk_digests, void* d_root, void* stream) {
-    if (!c || dev < 0 || dev >= (int)c->devs.size() || !tree_params_ok(chunk, leaf) || !d_root)
+    Tree t;
+    if (!c || dev < 0 || dev >= (int)c->devs.size() || !tree_resolve(tp, &t) || !d_root)
         return fail(MXD_ERR_INVALID, "dev_tree_digest: bad arguments");
     DeviceGuard guard(c->devs[dev]->ordinal);
     cudaStream_t st = (cudaStream_t)stream;
-    const uint64_t nchunks = size ? (size + chunk - 1) / chunk : 1;
+    const uint64_t nchunks = size ? (size + t.chunk - 1) / t.chunk : 1;
     uint8_t* chunks = static_cast<uint8_t*>(d_chunk_digests);
     uint8_t* owned = nullptr;
     if (!chunks) { MXD_CUDA(cudaMallocAsync(&owned, nchunks * 32, st)); chunks = owned; }
-    int rc = enqueue_tree_chunks(c, static_cast<const uint8_t*>(d_data), size, chunk, leaf, chunks, st);
-    if (rc == MXD_OK) rc = enqueue_tree_finish(c, chunks, nchunks, size, chunk, leaf, static_cast<uint8_t*>(d_root), st);
+    int rc = enqueue_tree_chunks(c, t, static_cast<const uint8_t*>(d_data), size, chunks, st);
+    if (rc == MXD_OK) rc = enqueue_tree_finish(c, t, chunks, nchunks, size, static_cast<uint8_t*>(d_root), st);
     if (owned) cudaFreeAsync(owned, st);
     return rc;
 }
@@ -643,9 +730,10 @@ int mxd_dev_gen_fill(mxd_ctx* c, int dev, void* d_dst, uint64_t offset, uint64_t
     return MXD_OK;
 }
 
-int mxd_tree_chunks(mxd_ctx* c, const void* piece, uint64_t nbytes, uint64_t chunk, uint64_t leaf, uint8_t* out) {
-    if (!c || !tree_params_ok(chunk, leaf) || !out || (nbytes && !piece)) return fail(MXD_ERR_INVALID, "tree_chunks: bad arguments");
-    const uint64_t nchunks = nbytes ? (nbytes + chunk - 1) / chunk : 1;
+int mxd_tree_chunks(mxd_ctx* c, const void* piece, uint64_t nbytes, const mxd_tree_params* tp, uint8_t* out) {
+    Tree t;
+    if (!c || !tree_resolve(tp, &t) || !out || (nbytes && !piece)) return fail(MXD_ERR_INVALID, "tree_chunks: bad arguments");
+    const uint64_t nchunks = nbytes ? (nbytes + t.chunk - 1) / t.chunk : 1;
     int ord = -1;
     const MemKind kind = classify(piece, &ord);
     if (kind == MemKind::Device) {
@@ -656,7 +744,7 @@ int mxd_tree_chunks(mxd_ctx* c, const void* piece, uint64_t nbytes, uint64_t chu
         DeviceGuard guard(d->ordinal);
         uint8_t* d_chunks = nullptr;
         MXD_CUDA(cudaMalloc(&d_chunks, nchunks * 32));
-        int rc = enqueue_tree_chunks(c, static_cast<const uint8_t*>(piece), nbytes, chunk, leaf, d_chunks, d->compute);
+        int rc = enqueue_tree_chunks(c, t, static_cast<const uint8_t*>(piece), nbytes, d_chunks, d->compute);
         if (rc == MXD_OK) {
             cudaError_t e = cudaMemcpyAsync(out, d_chunks, nchunks * 32, cudaMemcpyDeviceToHost, d->compute);
             if (e == cudaSuccess) e = cudaStreamSynchronize(d->compute);
@@ -667,39 +755,42 @@ int mxd_tree_chunks(mxd_ctx* c, const void* piece, uint64_t nbytes, uint64_t chu
         return rc;
     }
     Source src; src.mem = static_cast<const uint8_t*>(piece); src.pinned = (kind == MemKind::Pinned);
-    return host_tree_chunks_all(c, src, nbytes, chunk, leaf, out);
+    return host_tree_chunks_all(c, t, src, nbytes, out);
 }
 
-int mxd_tree_finish(mxd_ctx* c, const uint8_t* chunk_digests, uint64_t nchunks, uint64_t size, uint64_t chunk,
-                    uint64_t leaf, uint8_t root[32]) {
-    if (!c || !tree_params_ok(chunk, leaf) || !chunk_digests || !root || nchunks == 0) return fail(MXD_ERR_INVALID, "tree_finish: bad arguments");
-    const uint64_t expect = size ? (size + chunk - 1) / chunk : 1;
+int mxd_tree_finish(mxd_ctx* c, const uint8_t* chunk_digests, uint64_t nchunks, uint64_t size, const mxd_tree_params* tp,
+                    uint8_t root[32]) {
+    Tree t;
+    if (!c || !tree_resolve(tp, &t) || !chunk_digests || !root || nchunks == 0) return fail(MXD_ERR_INVALID, "tree_finish: bad arguments");
+    const uint64_t expect = size ? (size + t.chunk - 1) / t.chunk : 1;
     if (expect != nchunks) return fail(MXD_ERR_INVALID, "tree_finish: nchunks does not match size/chunk");
-    return host_tree_finish(c, c->devs[0], chunk_digests, nchunks, size, chunk, leaf, root);
+    return host_tree_finish(c, c->devs[0], t, chunk_digests, nchunks, size, root);
 }
 
-int mxd_tree_digest(mxd_ctx* c, const void* data, uint64_t size, uint64_t chunk, uint64_t leaf, uint8_t* chunk_digests,
+int mxd_tree_digest(mxd_ctx* c, const void* data, uint64_t size, const mxd_tree_params* tp, uint8_t* chunk_digests,
                     uint64_t* nchunks_out, uint8_t root[32]) {
-    if (!c || !tree_params_ok(chunk, leaf) || !root || (size && !data)) return fail(MXD_ERR_INVALID, "tree_digest: bad arguments");
-    const uint64_t nchunks = size ? (size + chunk - 1) / chunk : 1;
+    Tree t;
+    if (!c || !tree_resolve(tp, &t) || !root || (size && !data)) return fail(MXD_ERR_INVALID, "tree_digest: bad arguments");
+    const uint64_t nchunks = size ? (size + t.chunk - 1) / t.chunk : 1;
     std::vector<uint8_t> tmp;
     uint8_t* chunks = chunk_digests;
     if (!chunks) { tmp.resize(nchunks * 32); chunks = tmp.data(); }
-    int rc = mxd_tree_chunks(c, data, size, chunk, leaf, chunks);
+    int rc = mxd_tree_chunks(c, data, size, tp, chunks);
     if (rc != MXD_OK) return rc;
     if (nchunks_out) *nchunks_out = nchunks;
-    return host_tree_finish(c, c->devs[0], chunks, nchunks, size, chunk, leaf, root);
+    return host_tree_finish(c, c->devs[0], t, chunks, nchunks, size, root);
 }
 
-int mxd_tree_digest_file(mxd_ctx* c, const char* path, uint64_t chunk, uint64_t leaf, uint8_t* chunk_digests,
+int mxd_tree_digest_file(mxd_ctx* c, const char* path, const mxd_tree_params* tp, uint8_t* chunk_digests,
                          uint64_t cap_chunks, uint64_t* nchunks_out, uint64_t* size_out, uint8_t root[32]) {
-    if (!c || !path || !tree_params_ok(chunk, leaf) || !root) return fail(MXD_ERR_INVALID, "tree_digest_file: bad arguments");
+    Tree t;
+    if (!c || !path || !tree_resolve(tp, &t) || !root) return fail(MXD_ERR_INVALID, "tree_digest_file: bad arguments");
     int fd = open(path, O_RDONLY | O_CLOEXEC);
     if (fd < 0) return fail(MXD_ERR_IO, std::string("open ") + path + ": " + strerror(errno));
     struct stat st;
     if (fstat(fd, &st) != 0) { int e = errno; close(fd); errno = e; return fail(MXD_ERR_IO, std::string("fstat: ") + strerror(e)); }
     const uint64_t size = (uint64_t)st.st_size;
-    const uint64_t nchunks = size ? (size + chunk - 1) / chunk : 1;
+    const uint64_t nchunks = size ? (size + t.chunk - 1) / t.chunk : 1;
     if (size_out) *size_out = size;
     if (nchunks_out) *nchunks_out = nchunks;
     if (chunk_digests && cap_chunks < nchunks) { close(fd); return fail(MXD_ERR_INVALID, "tree_digest_file: chunk_digests too small"); }
@@ -707,10 +798,10 @@ int mxd_tree_digest_file(mxd_ctx* c, const char* path, uint64_t chunk, uint64_t 
     uint8_t* chunks = chunk_digests;
     if (!chunks) { tmp.resize(nchunks * 32); chunks = tmp.data(); }
     Source src; src.fd = fd;
-    int rc = host_tree_chunks_all(c, src, size, chunk, leaf, chunks);
+    int rc = host_tree_chunks_all(c, t, src, size, chunks);
     close(fd);
     if (rc != MXD_OK) return rc;
-    return host_tree_finish(c, c->devs[0], chunks, nchunks, size, chunk, leaf, root);
+    return host_tree_finish(c, c->devs[0], t, chunks, nchunks, size, root);
 }
 
 // ---- whole-message digests ---------------------------------------------------------------------------

@@ -11,6 +11,11 @@ from . import _native as N
 
 DEFAULT_CHUNK = 8 << 20   # bytes covered by one chunk digest (the list a manifest carries)
 DEFAULT_LEAF = 16 << 10   # bytes hashed by one GPU lane at the bottom of the tree
+DEFAULT_FANOUT = 8        # digests per upper-level node; chunk = leaf * fanout**k
+
+
+def _tp(chunk: int, leaf: int, fanout: int):
+    return C.byref(N.TreeParams(chunk, leaf, fanout, 0))
 
 
 def _buf(data):
@@ -64,9 +69,11 @@ def server_part_count(size: int, force_multipart: bool = False) -> int:
     return int(N.load().mxd_server_part_count(size, 1 if force_multipart else 0))
 
 
-def tree_shape(size: int, chunk: int = DEFAULT_CHUNK, leaf: int = DEFAULT_LEAF) -> List[int]:
-    counts = (C.c_uint64 * 64)()
-    lv = N.load().mxd_tree_shape(size, chunk, leaf, counts, 64)
+def tree_shape(size: int, chunk: int = DEFAULT_CHUNK, leaf: int = DEFAULT_LEAF, fanout: int = DEFAULT_FANOUT) -> List[int]:
+    """Node count per level, leaves first (level k, where chunk = leaf*fanout**k, is the chunk list)."""
+    counts = (C.c_uint64 * 80)()
+    klevel = C.c_int()
+    lv = N.load().mxd_tree_shape(size, _tp(chunk, leaf, fanout), counts, 80, C.byref(klevel))
     if lv < 0:
         raise N.MxdError(lv, "mxd_tree_shape")
     return [int(counts[i]) for i in range(lv)]
@@ -112,6 +119,14 @@ class Engine:
         N.check(self._lib.mxd_get_stats(self._ctx, C.byref(st)), "mxd_get_stats")
         return {"kernel_launches": st.kernel_launches, "bytes_hashed": st.bytes_hashed,
                 "h2d_bytes": st.h2d_bytes, "d2h_bytes": st.d2h_bytes}
+
+    def prof_enable(self, on: bool = True):
+        N.check(self._lib.mxd_prof_enable(self._ctx, 1 if on else 0), "mxd_prof_enable")
+
+    def prof_read(self) -> dict:
+        ms, n, b = C.c_double(), C.c_uint64(), C.c_uint64()
+        N.check(self._lib.mxd_prof_read(self._ctx, C.byref(ms), C.byref(n), C.byref(b)), "mxd_prof_read")
+        return {"kernel_ms": ms.value, "launches": n.value, "bytes": b.value}
 
     def cancel(self):
         self._lib.mxd_cancel(self._ctx)
@@ -194,21 +209,24 @@ class Engine:
         return Hasher(self)
 
     # -- tree digests ------------------------------------------------------------------------
-    def tree_digest(self, data, chunk: int = DEFAULT_CHUNK, leaf: int = DEFAULT_LEAF):
+    def tree_digest(self, data, chunk: int = DEFAULT_CHUNK, leaf: int = DEFAULT_LEAF, fanout: int = DEFAULT_FANOUT):
         """-> (chunk_digests: list[bytes], root: bytes) for a bytes-like blob in host memory."""
         addr, n, keep = _buf(data)
-        return self.tree_digest_ptr(addr, n, chunk, leaf)
+        return self.tree_digest_ptr(addr, n, chunk, leaf, fanout)
 
-    def tree_digest_ptr(self, ptr: int, n: int, chunk: int = DEFAULT_CHUNK, leaf: int = DEFAULT_LEAF):
+    def tree_digest_ptr(self, ptr: int, n: int, chunk: int = DEFAULT_CHUNK, leaf: int = DEFAULT_LEAF,
+                        fanout: int = DEFAULT_FANOUT):
         nch = max(1, -(-n // chunk))
         chunks = (C.c_uint8 * (32 * nch))()
         got = C.c_uint64()
         root = (C.c_uint8 * 32)()
-        N.check(self._lib.mxd_tree_digest(self._ctx, ptr, n, chunk, leaf, chunks, C.byref(got), root), "mxd_tree_digest")
+        N.check(self._lib.mxd_tree_digest(self._ctx, ptr, n, _tp(chunk, leaf, fanout), chunks, C.byref(got), root),
+                "mxd_tree_digest")
         raw = bytes(chunks)
         return [raw[32 * i:32 * i + 32] for i in range(got.value)], bytes(root)
 
-    def tree_digest_file(self, path: str, chunk: int = DEFAULT_CHUNK, leaf: int = DEFAULT_LEAF):
+    def tree_digest_file(self, path: str, chunk: int = DEFAULT_CHUNK, leaf: int = DEFAULT_LEAF,
+                         fanout: int = DEFAULT_FANOUT):
         import os
         size = os.stat(path).st_size
         nch = max(1, -(-size // chunk))
@@ -216,26 +234,28 @@ class Engine:
         got = C.c_uint64()
         sz = C.c_uint64()
         root = (C.c_uint8 * 32)()
-        N.check(self._lib.mxd_tree_digest_file(self._ctx, path.encode(), chunk, leaf, chunks, nch, C.byref(got),
-                                               C.byref(sz), root), "mxd_tree_digest_file")
+        N.check(self._lib.mxd_tree_digest_file(self._ctx, path.encode(), _tp(chunk, leaf, fanout), chunks, nch,
+                                               C.byref(got), C.byref(sz), root), "mxd_tree_digest_file")
         raw = bytes(chunks)
         return [raw[32 * i:32 * i + 32] for i in range(got.value)], bytes(root), sz.value
 
-    def tree_chunks_ptr(self, ptr: int, n: int, chunk: int = DEFAULT_CHUNK, leaf: int = DEFAULT_LEAF) -> bytes:
+    def tree_chunks_ptr(self, ptr: int, n: int, chunk: int = DEFAULT_CHUNK, leaf: int = DEFAULT_LEAF,
+                        fanout: int = DEFAULT_FANOUT) -> bytes:
         nch = max(1, -(-n // chunk))
         chunks = (C.c_uint8 * (32 * nch))()
-        N.check(self._lib.mxd_tree_chunks(self._ctx, ptr, n, chunk, leaf, chunks), "mxd_tree_chunks")
+        N.check(self._lib.mxd_tree_chunks(self._ctx, ptr, n, _tp(chunk, leaf, fanout), chunks), "mxd_tree_chunks")
         return bytes(chunks)
 
-    def tree_chunks(self, data, chunk: int = DEFAULT_CHUNK, leaf: int = DEFAULT_LEAF) -> bytes:
+    def tree_chunks(self, data, chunk: int = DEFAULT_CHUNK, leaf: int = DEFAULT_LEAF, fanout: int = DEFAULT_FANOUT) -> bytes:
         addr, n, keep = _buf(data)
-        return self.tree_chunks_ptr(addr, n, chunk, leaf)
+        return self.tree_chunks_ptr(addr, n, chunk, leaf, fanout)
 
-    def tree_finish(self, chunk_digests: bytes, size: int, chunk: int = DEFAULT_CHUNK, leaf: int = DEFAULT_LEAF) -> bytes:
+    def tree_finish(self, chunk_digests: bytes, size: int, chunk: int = DEFAULT_CHUNK, leaf: int = DEFAULT_LEAF,
+                    fanout: int = DEFAULT_FANOUT) -> bytes:
         n = len(chunk_digests) // 32
         arr = (C.c_uint8 * len(chunk_digests)).from_buffer_copy(chunk_digests)
         root = (C.c_uint8 * 32)()
-        N.check(self._lib.mxd_tree_finish(self._ctx, arr, n, size, chunk, leaf, root), "mxd_tree_finish")
+        N.check(self._lib.mxd_tree_finish(self._ctx, arr, n, size, _tp(chunk, leaf, fanout), root), "mxd_tree_finish")
         return bytes(root)
 
     # -- device-resident asynchronous forms (raw device pointers, cudaStream_t as int) -----------
@@ -245,14 +265,15 @@ class Engine:
     def dev_sha256_batch(self, dev: int, d_spans: int, n: int, d_out: int, stream: int = 0):
         N.check(self._lib.mxd_dev_sha256_batch(self._ctx, dev, d_spans, n, d_out, stream), "mxd_dev_sha256_batch")
 
-    def dev_tree_chunks(self, dev: int, d_piece: int, nbytes: int, chunk: int, leaf: int, d_chunks: int, stream: int = 0):
-        N.check(self._lib.mxd_dev_tree_chunks(self._ctx, dev, d_piece, nbytes, chunk, leaf, d_chunks, stream), "mxd_dev_tree_chunks")
+    def dev_tree_chunks(self, dev: int, d_piece: int, nbytes: int, tp: Tuple[int, int, int], d_chunks: int, stream: int = 0):
+        """tp = (chunk, leaf, fanout)"""
+        N.check(self._lib.mxd_dev_tree_chunks(self._ctx, dev, d_piece, nbytes, _tp(*tp), d_chunks, stream), "mxd_dev_tree_chunks")
 
-    def dev_tree_finish(self, dev: int, d_chunks: int, nchunks: int, size: int, chunk: int, leaf: int, d_root: int, stream: int = 0):
-        N.check(self._lib.mxd_dev_tree_finish(self._ctx, dev, d_chunks, nchunks, size, chunk, leaf, d_root, stream), "mxd_dev_tree_finish")
+    def dev_tree_finish(self, dev: int, d_chunks: int, nchunks: int, size: int, tp: Tuple[int, int, int], d_root: int, stream: int = 0):
+        N.check(self._lib.mxd_dev_tree_finish(self._ctx, dev, d_chunks, nchunks, size, _tp(*tp), d_root, stream), "mxd_dev_tree_finish")
 
-    def dev_tree_digest(self, dev: int, d_data: int, size: int, chunk: int, leaf: int, d_chunks: int, d_root: int, stream: int = 0):
-        N.check(self._lib.mxd_dev_tree_digest(self._ctx, dev, d_data, size, chunk, leaf, d_chunks, d_root, stream), "mxd_dev_tree_digest")
+    def dev_tree_digest(self, dev: int, d_data: int, size: int, tp: Tuple[int, int, int], d_chunks: int, d_root: int, stream: int = 0):
+        N.check(self._lib.mxd_dev_tree_digest(self._ctx, dev, d_data, size, _tp(*tp), d_chunks, d_root, stream), "mxd_dev_tree_digest")
 
     def dev_compare(self, dev: int, d_got: int, d_want: int, n: int, d_ok: int, stream: int = 0):
         N.check(self._lib.mxd_dev_compare(self._ctx, dev, d_got, d_want, n, d_ok, stream), "mxd_dev_compare")

@@ -92,23 +92,32 @@ int64_t orc_server_part_count(int64_t size, int force_multipart) {
 }
 
 /* ------------------------------------------------------------------------------------------
- * New in modelx-b200: tree digest "modelx.tree.v1" (DESIGN.md section 3).
+ * New in modelx-b200: tree digest "modelx.tree.v1" (DESIGN.md section 3), parameters
+ * (leaf, fanout, chunk = leaf * fanout^k, k >= 1).
  *   level 0: leaf i = bytes [i*leaf, min((i+1)*leaf, size)), n0 = max(1, ceil(size/leaf))
- *   level k+1: node j = SHA256(concat of level-k digests j*fanout .. min((j+1)*fanout, n_k)-1)
- *   level 1 always exists (the "chunk" digests, each covering leaf*fanout bytes); further levels
- *   are added while a level has more than one node.
+ *   level j+1: node i = SHA256(concat of level-j digests i*fanout .. min((i+1)*fanout, n_j)-1)
+ *   levels are built at least up to level k (the CHUNK digests, each covering `chunk` bytes) and
+ *   further while a level has more than one node.
  *   root = SHA256(magic16 || LE64(size) || LE64(leaf) || LE32(fanout) || LE32(0) || top)
  * ---------------------------------------------------------------------------------------- */
-int orc_tree_shape(uint64_t size, uint64_t leaf, uint32_t fanout, uint64_t counts[], int max_levels) {
-    if (leaf == 0 || fanout < 2 || max_levels < 2) return -1;
+static int tree_klevel(uint64_t leaf, uint32_t fanout, uint64_t chunk) {
+    if (leaf == 0 || fanout < 2 || chunk < leaf) return -1;
+    uint64_t span = leaf; int k = 0;
+    while (span < chunk) { if (span > chunk / fanout) return -1; span *= fanout; ++k; }
+    return (span == chunk && k >= 1) ? k : -1;
+}
+
+int orc_tree_shape(uint64_t size, uint64_t leaf, uint32_t fanout, uint64_t chunk, uint64_t counts[], int max_levels) {
+    int k = tree_klevel(leaf, fanout, chunk);
+    if (k < 0 || max_levels < 2) return -1;
     uint64_t n = size ? (size + leaf - 1) / leaf : 1;
     int lv = 0;
     counts[lv++] = n;
-    do {
+    while (lv <= k || n > 1) {
         if (lv >= max_levels) return -1;
         n = (n + fanout - 1) / fanout;
         counts[lv++] = n;
-    } while (n > 1);
+    }
     return lv;
 }
 
@@ -179,10 +188,11 @@ void orc_tree_root(uint64_t size, uint64_t leaf, uint32_t fanout, const uint8_t 
     orc_sha256(m, sizeof m, root);
 }
 
-int orc_tree_digest(const void* data, uint64_t size, uint64_t leaf, uint32_t fanout, int threads,
+int orc_tree_digest(const void* data, uint64_t size, uint64_t leaf, uint32_t fanout, uint64_t chunk, int threads,
                     uint8_t* chunk_digests, uint64_t* nchunks, uint8_t top[32], uint8_t root[32]) {
-    uint64_t counts[64];
-    int levels = orc_tree_shape(size, leaf, fanout, counts, 64);
+    uint64_t counts[80];
+    int k = tree_klevel(leaf, fanout, chunk);
+    int levels = orc_tree_shape(size, leaf, fanout, chunk, counts, 80);
     if (levels < 0) return -1;
     uint8_t* cur = (uint8_t*)malloc(32 * counts[0]);
     if (!cur) return -ENOMEM;
@@ -192,9 +202,9 @@ int orc_tree_digest(const void* data, uint64_t size, uint64_t leaf, uint32_t fan
         if (!nxt) { free(cur); return -ENOMEM; }
         orc_hash_segments(cur, 32 * counts[lv - 1], 32ull * fanout, threads, nxt);
         free(cur); cur = nxt;
-        if (lv == 1) {
-            if (chunk_digests) memcpy(chunk_digests, cur, 32 * counts[1]);
-            if (nchunks) *nchunks = counts[1];
+        if (lv == k) {
+            if (chunk_digests) memcpy(chunk_digests, cur, 32 * counts[lv]);
+            if (nchunks) *nchunks = counts[lv];
         }
     }
     if (top) memcpy(top, cur, 32);

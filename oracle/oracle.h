@@ -51,11 +51,11 @@ int64_t orc_server_part_count(int64_t size, int force_multipart);
 /* --- definitions that are NEW in modelx-b200 (no reference counterpart) ---------------
  * Spec restated on the CPU so the GPU implementation has an independent check.  Every node of
  * the tree is a plain SHA-256 of well-defined bytes. */
-/* number of nodes per level; returns the number of levels (>= 2: leaves + chunk level). */
-int orc_tree_shape(uint64_t size, uint64_t leaf, uint32_t fanout, uint64_t counts[], int max_levels);
-/* chunk_digests: level-1 nodes (each covers leaf*fanout bytes), may be NULL.
+/* number of nodes per level; returns the number of levels (>= k+1 where chunk = leaf*fanout^k). */
+int orc_tree_shape(uint64_t size, uint64_t leaf, uint32_t fanout, uint64_t chunk, uint64_t counts[], int max_levels);
+/* chunk_digests: level-k nodes (each covers `chunk` bytes), may be NULL.
  * top: digest of the single node of the last level.  root: final blob identity. */
-int orc_tree_digest(const void* data, uint64_t size, uint64_t leaf, uint32_t fanout, int threads,
+int orc_tree_digest(const void* data, uint64_t size, uint64_t leaf, uint32_t fanout, uint64_t chunk, int threads,
                     uint8_t* chunk_digests, uint64_t* nchunks, uint8_t top[32], uint8_t root[32]);
 void orc_tree_root(uint64_t size, uint64_t leaf, uint32_t fanout, const uint8_t top[32], uint8_t root[32]);
 /* one level of the tree: out[j] = SHA256(in[j*seg .. min((j+1)*seg, n))), threaded. */

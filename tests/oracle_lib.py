@@ -41,8 +41,8 @@ class Oracle:
         L.orc_calc_parts.argtypes = [C.c_int64, C.c_int64, C.POINTER(_Part)]
         L.orc_server_part_count.argtypes = [C.c_int64, C.c_int]
         L.orc_server_part_count.restype = C.c_int64
-        L.orc_tree_shape.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64), C.c_int]
-        L.orc_tree_digest.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, u8p,
+        L.orc_tree_shape.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint64, C.POINTER(C.c_uint64), C.c_int]
+        L.orc_tree_digest.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint64, C.c_int, u8p,
                                       C.POINTER(C.c_uint64), u8p, u8p]
         L.orc_tree_root.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, u8p, u8p]
         L.orc_hash_segments.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, u8p]
@@ -105,12 +105,14 @@ class Oracle:
         return int(self.L.orc_server_part_count(size, 1 if force else 0))
 
     # --- tree (modelx-b200's own definition, restated on the CPU) ---------------------------------
-    def tree_shape(self, size: int, leaf: int, fanout: int) -> List[int]:
-        counts = (C.c_uint64 * 64)()
-        lv = self.L.orc_tree_shape(size, leaf, fanout, counts, 64)
+    def tree_shape(self, size: int, chunk: int, leaf: int, fanout: int) -> List[int]:
+        counts = (C.c_uint64 * 80)()
+        lv = self.L.orc_tree_shape(size, leaf, fanout, chunk, counts, 80)
+        if lv < 0:
+            raise ValueError("bad tree parameters")
         return [int(counts[i]) for i in range(lv)]
 
-    def tree_digest(self, data, leaf: int, fanout: int, threads: int = 8):
+    def tree_digest(self, data, chunk: int, leaf: int, fanout: int, threads: int = 8):
         """-> (chunk_digests list, top, root)"""
         if isinstance(data, (bytes, bytearray)):
             n = len(data)
@@ -119,16 +121,17 @@ class Oracle:
         else:  # numpy
             n = data.nbytes
             ptr = data.ctypes.data
-        return self.tree_digest_ptr(ptr, n, leaf, fanout, threads)
+        return self.tree_digest_ptr(ptr, n, chunk, leaf, fanout, threads)
 
-    def tree_digest_ptr(self, ptr: int, n: int, leaf: int, fanout: int, threads: int = 8):
-        nch = max(1, -(-n // (leaf * fanout)))
+    def tree_digest_ptr(self, ptr: int, n: int, chunk: int, leaf: int, fanout: int, threads: int = 8):
+        nch = max(1, -(-n // chunk))
         chunks = (C.c_uint8 * (32 * nch))()
         got = C.c_uint64()
         top = (C.c_uint8 * 32)()
         root = (C.c_uint8 * 32)()
-        rc = self.L.orc_tree_digest(ptr, n, leaf, fanout, threads, chunks, C.byref(got), top, root)
-        assert rc == 0
+        rc = self.L.orc_tree_digest(ptr, n, leaf, fanout, chunk, threads, chunks, C.byref(got), top, root)
+        if rc != 0:
+            raise ValueError("bad tree parameters")
         raw = bytes(chunks)
         return [raw[32 * i:32 * i + 32] for i in range(got.value)], bytes(top), bytes(root)
 

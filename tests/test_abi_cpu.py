@@ -57,11 +57,14 @@ def test_digest_string_roundtrip(oracle):
 
 def test_tree_shape_matches_oracle(oracle):
     for size in (0, 1, 16384, 16385, 8 << 20, (8 << 20) + 1, 10 ** 10, 10 ** 11, 14 * 10 ** 10):
-        for chunk, leaf in ((8 << 20, 16 << 10), (8 << 20, 64 << 10), (1 << 20, 4096), (128, 64)):
-            assert modelx_b200.tree_shape(size, chunk, leaf) == oracle.tree_shape(size, leaf, chunk // leaf)
-    for chunk, leaf in ((100, 64), (64, 64), (8 << 20, 100), (0, 64)):
+        for chunk, leaf, fanout in ((8 << 20, 16 << 10, 8), (8 << 20, 16 << 10, 512), (8 << 20, 64 << 10, 2),
+                                    (1 << 20, 4096, 16), (128, 64, 2), (8 << 20, 4096, 2048)):
+            assert modelx_b200.tree_shape(size, chunk, leaf, fanout) == oracle.tree_shape(size, chunk, leaf, fanout)
+    assert modelx_b200.tree_shape(10 ** 11) == [6103516, 762940, 95368, 11921, 1491, 187, 24, 3, 1]
+    for chunk, leaf, fanout in ((100, 64, 2), (64, 64, 2), (8 << 20, 100, 8), (0, 64, 2), (8 << 20, 16 << 10, 16),
+                                (8 << 20, 16 << 10, 1)):
         with pytest.raises(modelx_b200.MxdError):
-            modelx_b200.tree_shape(1000, chunk, leaf)
+            modelx_b200.tree_shape(1000, chunk, leaf, fanout)
 
 
 def test_no_cpu_fallback_without_cuda():

@@ -143,21 +143,29 @@ def test_file_digests_match_reference_path(engine, oracle, tmp_path):
 # ------------------------------------------------------------------------------------------------
 # chunked tree digest
 # ------------------------------------------------------------------------------------------------
-TREE_CASES = [  # (size, chunk, leaf)
-    (0, 128, 64), (1, 128, 64), (63, 128, 64), (64, 128, 64), (65, 128, 64), (128, 128, 64), (129, 128, 64),
-    (1000, 256, 64), (100_000, 4096, 1024), (262_144, 16384, 1024), (262_145, 16384, 1024),
-    ((1 << 20) - 1, 1 << 18, 1 << 12), (1 << 20, 1 << 18, 1 << 12), ((1 << 20) + 1, 1 << 18, 1 << 12),
-    (20_000_003, 1 << 20, 16 << 10), (50_000_000, 8 << 20, 16 << 10), (50_000_000, 8 << 20, 64 << 10),
+TREE_CASES = [  # (size, chunk, leaf, fanout)
+    (0, 128, 64, 2), (1, 128, 64, 2), (63, 128, 64, 2), (64, 128, 64, 2), (65, 128, 64, 2), (128, 128, 64, 2),
+    (129, 128, 64, 2), (1000, 256, 64, 4), (1000, 256, 64, 2), (100_000, 4096, 1024, 4), (262_144, 16384, 1024, 16),
+    (262_145, 16384, 1024, 4), ((1 << 20) - 1, 1 << 18, 1 << 12, 8), (1 << 20, 1 << 18, 1 << 12, 64),
+    ((1 << 20) + 1, 1 << 18, 1 << 12, 2), (20_000_003, 1 << 20, 16 << 10, 8), (50_000_000, 8 << 20, 16 << 10, 8),
+    (50_000_000, 8 << 20, 16 << 10, 512), (50_000_000, 8 << 20, 64 << 10, 2), (50_000_000, 8 << 20, 4 << 10, 2048),
 ]
 
 
-@pytest.mark.parametrize("size,chunk,leaf", TREE_CASES)
-def test_tree_digest_host_vs_oracle(engine, oracle, size, chunk, leaf):
+@pytest.mark.parametrize("size,chunk,leaf,fanout", TREE_CASES)
+def test_tree_digest_host_vs_oracle(engine, oracle, size, chunk, leaf, fanout):
     blob = oracle.gen(7, size, SEED)
-    chunks, root = engine.tree_digest(blob, chunk, leaf)
-    want_chunks, _, want_root = oracle.tree_digest(blob, leaf, chunk // leaf)
+    chunks, root = engine.tree_digest(blob, chunk, leaf, fanout)
+    want_chunks, _, want_root = oracle.tree_digest(blob, chunk, leaf, fanout)
     assert chunks == want_chunks
     assert root == want_root
+
+
+def test_tree_default_params(engine, oracle):
+    blob = oracle.gen(0, 20_000_000, SEED + 9)
+    chunks, root = engine.tree_digest(blob)          # 8 MiB chunks, 16 KiB leaves, fan-out 8
+    want_chunks, _, want_root = oracle.tree_digest(blob, 8 << 20, 16 << 10, 8)
+    assert (chunks, root) == (want_chunks, want_root) and len(chunks) == 3
 
 
 def test_tree_digest_streams_through_small_ring(oracle):
@@ -165,9 +173,9 @@ def test_tree_digest_streams_through_small_ring(oracle):
     size = 40_000_000 + 77
     blob = oracle.gen(0, size, SEED + 1)
     with modelx_b200.Engine(devices=[0], ring_bytes=4 << 20) as eng:
-        chunks, root = eng.tree_digest(blob, 8 << 20, 16 << 10)
+        chunks, root = eng.tree_digest(blob, 8 << 20, 16 << 10, 8)
         st = eng.stats()
-    want_chunks, _, want_root = oracle.tree_digest(blob, 16 << 10, 512)
+    want_chunks, _, want_root = oracle.tree_digest(blob, 8 << 20, 16 << 10, 8)
     assert chunks == want_chunks and root == want_root
     assert st["h2d_bytes"] >= size and st["kernel_launches"] >= 40
 
@@ -177,14 +185,14 @@ def test_tree_digest_file_and_pinned(engine, oracle, tmp_path):
     blob = oracle.gen(0, size, SEED + 2)
     p = tmp_path / "model.safetensors"
     p.write_bytes(blob)
-    want_chunks, _, want_root = oracle.tree_digest(blob, 16 << 10, 512)
-    chunks, root, sz = engine.tree_digest_file(str(p), 8 << 20, 16 << 10)
+    want_chunks, _, want_root = oracle.tree_digest(blob, 8 << 20, 16 << 10, 8)
+    chunks, root, sz = engine.tree_digest_file(str(p))
     assert (chunks, root, sz) == (want_chunks, want_root, size)
     # same bytes from pinned host memory (zero-copy H2D path)
     import ctypes
     ptr = engine.host_alloc(size)
     ctypes.memmove(ptr, blob, size)
-    chunks2, root2 = engine.tree_digest_ptr(ptr, size, 8 << 20, 16 << 10)
+    chunks2, root2 = engine.tree_digest_ptr(ptr, size)
     engine.host_free(ptr)
     assert (chunks2, root2) == (want_chunks, want_root)
 
@@ -192,18 +200,18 @@ def test_tree_digest_file_and_pinned(engine, oracle, tmp_path):
 def test_tree_sharded_equals_whole(engine, oracle):
     """Chunk ranges hashed independently (what each rank does) + finish == one-shot digest."""
     size = 9 * (1 << 20) + 4321
-    chunk, leaf = 1 << 20, 16 << 10
+    chunk, leaf, fanout = 1 << 20, 16 << 10, 8
     blob = oracle.gen(0, size, SEED + 3)
-    whole_chunks, whole_root = engine.tree_digest(blob, chunk, leaf)
+    whole_chunks, whole_root = engine.tree_digest(blob, chunk, leaf, fanout)
     nch = len(whole_chunks)
     for world in (2, 3, 4):
         gathered = b""
         for r in range(world):
             c0, c1 = nch * r // world, nch * (r + 1) // world
             piece = blob[c0 * chunk:min(c1 * chunk, size)]
-            gathered += engine.tree_chunks(piece, chunk, leaf)[:32 * (c1 - c0)]
+            gathered += engine.tree_chunks(piece, chunk, leaf, fanout)[:32 * (c1 - c0)]
         assert gathered == b"".join(whole_chunks)
-        assert engine.tree_finish(gathered, size, chunk, leaf) == whole_root
+        assert engine.tree_finish(gathered, size, chunk, leaf, fanout) == whole_root
 
 
 def test_device_generator_matches_oracle(engine, oracle):
@@ -219,17 +227,17 @@ def test_device_resident_tree_async(engine, oracle):
     """mxd_dev_* forms on the caller's stream: data generated in HBM, digests left in HBM."""
     torch = _torch()
     size = 100_000_000
-    chunk, leaf = 8 << 20, 16 << 10
+    chunk, leaf, fanout = 8 << 20, 16 << 10, 8
     nch = -(-size // chunk)
     data = torch.empty(size, dtype=torch.uint8, device="cuda")
     d_chunks = torch.empty(nch * 32, dtype=torch.uint8, device="cuda")
     d_root = torch.empty(32, dtype=torch.uint8, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
     engine.dev_gen_fill(0, data.data_ptr(), 0, size, SEED, st)
-    engine.dev_tree_digest(0, data.data_ptr(), size, chunk, leaf, d_chunks.data_ptr(), d_root.data_ptr(), st)
+    engine.dev_tree_digest(0, data.data_ptr(), size, (chunk, leaf, fanout), d_chunks.data_ptr(), d_root.data_ptr(), st)
     torch.cuda.synchronize()
     host = data.cpu().numpy()
-    want_chunks, _, want_root = oracle.tree_digest_ptr(host.ctypes.data, size, leaf, chunk // leaf, threads=32)
+    want_chunks, _, want_root = oracle.tree_digest_ptr(host.ctypes.data, size, chunk, leaf, fanout, threads=32)
     assert d_chunks.cpu().numpy().tobytes() == b"".join(want_chunks)
     assert d_root.cpu().numpy().tobytes() == want_root
     # compare kernel: all equal, then flip one expected digest
@@ -248,17 +256,17 @@ def test_full_size_config2_10GB(engine, oracle):
     """BASELINE config 2: one 10 GB blob, HBM-resident.  Chunk list and root vs the threaded oracle."""
     torch = _torch()
     size = 10_000_000_000
-    chunk, leaf = 8 << 20, 16 << 10
+    chunk, leaf, fanout = 8 << 20, 16 << 10, 8
     nch = -(-size // chunk)
     data = torch.empty(size, dtype=torch.uint8, device="cuda")
     d_chunks = torch.empty(nch * 32, dtype=torch.uint8, device="cuda")
     d_root = torch.empty(32, dtype=torch.uint8, device="cuda")
     engine.dev_gen_fill(0, data.data_ptr(), 0, size, SEED)
-    engine.dev_tree_digest(0, data.data_ptr(), size, chunk, leaf, d_chunks.data_ptr(), d_root.data_ptr())
+    engine.dev_tree_digest(0, data.data_ptr(), size, (chunk, leaf, fanout), d_chunks.data_ptr(), d_root.data_ptr())
     torch.cuda.synchronize()
     host = data.cpu().numpy()
     del data
-    want_chunks, _, want_root = oracle.tree_digest_ptr(host.ctypes.data, size, leaf, chunk // leaf, threads=64)
+    want_chunks, _, want_root = oracle.tree_digest_ptr(host.ctypes.data, size, chunk, leaf, fanout, threads=64)
     assert nch == 1193 and len(want_chunks) == nch
     assert d_chunks.cpu().numpy().tobytes() == b"".join(want_chunks)
     assert d_root.cpu().numpy().tobytes() == want_root
@@ -271,14 +279,14 @@ def test_full_size_config2_10GB(engine, oracle):
 # ------------------------------------------------------------------------------------------------
 def test_concurrent_callers(engine, oracle):
     blobs = [oracle.gen(0, 3_000_000 + 1000 * i, SEED + 10 + i) for i in range(6)]
-    want = [oracle.tree_digest(b, 16 << 10, 64)[2] for b in blobs]
+    want = [oracle.tree_digest(b, 1 << 20, 16 << 10, 8)[2] for b in blobs]
     got = [None] * len(blobs)
     errs = []
 
     def work(i):
         try:
             for _ in range(3):
-                got[i] = engine.tree_digest(blobs[i], 1 << 20, 16 << 10)[1]
+                got[i] = engine.tree_digest(blobs[i], 1 << 20, 16 << 10, 8)[1]
                 assert engine.sha256(blobs[i][:1000]) == hashlib.sha256(blobs[i][:1000]).digest()
         except Exception as e:  # pragma: no cover
             errs.append(e)
@@ -294,7 +302,7 @@ def test_cancel(oracle):
     with modelx_b200.Engine(devices=[0], ring_bytes=4 << 20) as eng:
         eng.cancel()
         with pytest.raises(modelx_b200.MxdError) as ei:
-            eng.tree_digest(blob, 1 << 20, 16 << 10)
+            eng.tree_digest(blob, 1 << 20, 16 << 10, 8)
         assert ei.value.status == -6
         eng.reset_cancel()
-        assert eng.tree_digest(blob, 1 << 20, 16 << 10)[1] == oracle.tree_digest(blob, 16 << 10, 64)[2]
+        assert eng.tree_digest(blob, 1 << 20, 16 << 10, 8)[1] == oracle.tree_digest(blob, 1 << 20, 16 << 10, 8)[2]

@@ -105,20 +105,25 @@ def test_tree_definition_by_hand(oracle):
     """The oracle's tree digest equals the definition evaluated with hashlib."""
     import struct
     rng = random.Random(11)
-    for size, leaf, fanout in [(0, 64, 2), (1, 64, 2), (64, 64, 2), (1000, 128, 4), (100_000, 1024, 8), (262144, 1024, 16)]:
+    cases = [(0, 64, 2, 1), (1, 64, 2, 1), (64, 64, 2, 2), (1000, 128, 4, 1), (1000, 128, 4, 3),
+             (100_000, 1024, 8, 2), (262144, 1024, 16, 1), (300_000, 256, 2, 5)]
+    for size, leaf, fanout, k in cases:
+        chunk = leaf * fanout ** k
         data = rng.randbytes(size)
         level = [hashlib.sha256(data[i:i + leaf]).digest() for i in range(0, max(size, 1), leaf)]
-        chunks = None
-        while True:
+        chunks, lv = None, 0
+        while lv < k or len(level) > 1:
             level = [hashlib.sha256(b"".join(level[i:i + fanout])).digest() for i in range(0, len(level), fanout)]
-            if chunks is None:
+            lv += 1
+            if lv == k:
                 chunks = level
-            if len(level) == 1:
-                break
         top = level[0]
         root = hashlib.sha256(b"modelx.tree.v1\0\0" + struct.pack("<QQII", size, leaf, fanout, 0) + top).digest()
-        got_chunks, got_top, got_root = oracle.tree_digest(data, leaf, fanout)
-        assert got_chunks == chunks and got_top == top and got_root == root, (size, leaf, fanout)
+        got_chunks, got_top, got_root = oracle.tree_digest(data, chunk, leaf, fanout)
+        assert got_chunks == chunks and got_top == top and got_root == root, (size, leaf, fanout, k)
+        assert len(chunks) == max(1, -(-size // chunk))
+    with pytest.raises(ValueError):
+        oracle.tree_digest(b"x" * 100, 100, 64, 2)      # chunk is not leaf * fanout**k
 
 
 def test_generator_is_offset_consistent(oracle):
