@@ -71,13 +71,10 @@ __device__ __forceinline__ uint32_t big_sigma1(uint32_t x) { return xor3(rotr(x,
 __device__ __forceinline__ uint32_t small_sigma0(uint32_t x) { return xor3(rotr(x, 7), rotr(x, 18), x >> 3); }
 __device__ __forceinline__ uint32_t small_sigma1(uint32_t x) { return xor3(rotr(x, 17), rotr(x, 19), x >> 10); }
 
-// One 512-bit block.  w[16] holds the block as big-endian words and is clobbered (rolling
-// 16-word schedule kept in registers).  `one` must hold the value 1 (see add_fma).
-__device__ __forceinline__ void sha256_compress(uint32_t (&h)[8], uint32_t (&w)[16], uint32_t one) {
+// The 64 rounds on s[8] in place (no feed-forward).  w[16] holds the block as big-endian words and
+// is clobbered (rolling 16-word schedule kept in registers).  `one` must hold 1 (see add_fma).
+__device__ __forceinline__ void sha256_rounds(uint32_t (&s)[8], uint32_t (&w)[16], uint32_t one) {
     constexpr K256Table K = k256_table();
-    uint32_t s[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s[i] = h[i];
 #pragma unroll
     for (int t = 0; t < 64; ++t) {
         if (t >= 16) {
@@ -98,6 +95,14 @@ __device__ __forceinline__ void sha256_compress(uint32_t (&h)[8], uint32_t (&w)[
         uint32_t t2 = add_fma(big_sigma0(a), maj(a, b, c), one);
         hh = add_fma(t1, t2, one);                            // becomes a of the next round
     }
+}
+
+// One 512-bit block: rounds + feed-forward (FIPS 180-4 section 6.2.2 step 4).
+__device__ __forceinline__ void sha256_compress(uint32_t (&h)[8], uint32_t (&w)[16], uint32_t one) {
+    uint32_t s[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = h[i];
+    sha256_rounds(s, w, one);
 #pragma unroll
     for (int i = 0; i < 8; ++i) h[i] = add_fma(h[i], s[i], one);
 }

@@ -51,7 +51,7 @@ __device__ __forceinline__ void unpack_block(const uint4& v0, const uint4& v1, c
     w[12] = bswap32(v3.x); w[13] = bswap32(v3.y); w[14] = bswap32(v3.z); w[15] = bswap32(v3.w);
 }
 
-// MINB = resident CTAs per SM the register allocator must allow (8 -> 64 regs, 6 -> 80 regs).
+// MINB = resident CTAs per SM the register allocator must allow (6 -> 80 registers, 8 -> 63).
 template <int MINB>
 __global__ void __launch_bounds__(kThreads, MINB) k_sha256_lanes(const MsgJob j) {
     const uint64_t m = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
@@ -90,27 +90,31 @@ __global__ void __launch_bounds__(kThreads, MINB) k_sha256_lanes(const MsgJob j)
     const uint64_t nblk = live ? nfull + (fin ? (r >= 56 ? 2u : 1u) : 0u) : 0;
     const uint64_t bits = (prefix + len) << 3;
 
-    // Fast path when every lane of the warp has a 16-byte aligned message (always true for tree
-    // levels): 4 x LDG.128 per block, next block prefetched into registers while this one is
-    // compressed.  Lane i streams its own message, so each request touches 32 different lines but
-    // consumes whole 32-byte sectors: DRAM traffic equals the algorithmic bytes.
+    // Hot loop: when every lane of the warp has a 16-byte aligned message (always true for tree
+    // levels) the full blocks run in a straight-line loop of their own: 4 x LDG.128 per block, the
+    // next block prefetched into registers while this one is compressed.  Keeping this loop free of
+    // control-flow merges matters: after a merge ptxas must wait for every load that any incoming
+    // path may have in flight, which would serialise the prefetch with the compress (7.7 % of all
+    // stall samples in the first profile, profiles/r01_ncu_leaf_v1_summary.txt).
+    // Lane i streams its own message, so a request touches 32 different lines but consumes whole
+    // 32-byte sectors: DRAM traffic equals the algorithmic bytes.
     const bool warp_aligned = __all_sync(0xffffffffu, (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0);
-    const uint4* p4 = reinterpret_cast<const uint4*>(ptr);
-    uint4 v0, v1, v2, v3;
-    if (warp_aligned && nfull) { v0 = ldg128(p4); v1 = ldg128(p4 + 1); v2 = ldg128(p4 + 2); v3 = ldg128(p4 + 3); }
-
     uint32_t w[16];
-    for (uint64_t b = 0; b < nblk; ++b) {
+    uint64_t b = 0;
+    if (warp_aligned && live && nfull) {
+        const uint4* p4 = reinterpret_cast<const uint4*>(ptr);
+        uint4 v0 = ldg128(p4), v1 = ldg128(p4 + 1), v2 = ldg128(p4 + 2), v3 = ldg128(p4 + 3);
+        for (; b < nfull; ++b) {
+            unpack_block(v0, v1, v2, v3, w);
+            p4 += (b + 1 < nfull) ? 4 : 0;   // last iteration re-reads its own block (L1 hit) instead of branching
+            v0 = ldg128(p4); v1 = ldg128(p4 + 1); v2 = ldg128(p4 + 2); v3 = ldg128(p4 + 3);
+            sha256_compress(h, w, one);
+        }
+    }
+    // Everything else: unaligned full blocks, the padded tail block and the length block.
+    for (; b < nblk; ++b) {
         if (b < nfull) {
-            if (warp_aligned) {
-                unpack_block(v0, v1, v2, v3, w);
-                if (b + 1 < nfull) {
-                    p4 += 4;
-                    v0 = ldg128(p4); v1 = ldg128(p4 + 1); v2 = ldg128(p4 + 2); v3 = ldg128(p4 + 3);
-                }
-            } else {
-                load_block_unaligned(ptr + (b << 6), w);
-            }
+            load_block_unaligned(ptr + (b << 6), w);
         } else if (b == nfull) {
             // r tail bytes, the 0x80 marker, zeros; the length too when it fits (r < 56)
             const uint8_t* t = ptr + (nfull << 6);
@@ -146,6 +150,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_sha256_lanes(const MsgJob j)
     uint4* o = reinterpret_cast<uint4*>(j.out + 32 * m);
     o[0] = lo; o[1] = hi;
 }
+
 
 // One thread: the 72-byte root message of modelx.tree.v1 (two blocks with padding).
 __global__ void k_tree_root(uint64_t size, uint64_t leaf, uint32_t fanout, const uint8_t* __restrict__ top,
@@ -201,15 +206,17 @@ __global__ void k_gen_fill(uint64_t* __restrict__ dst, uint64_t first_word, uint
 
 }  // namespace
 
-// Occupancy variant (tuning knob, MXD_TUNE_MINB=6|8): 8 CTAs x 128 threads at <= 64 registers, or 6 at <= 80.
-static int g_minb = [] { const char* e = getenv("MXD_TUNE_MINB"); return (e && atoi(e) == 6) ? 6 : 8; }();
+// Occupancy: 6 CTAs x 128 threads per SM (80 registers, 24 warps) is the default; 4..6 CTAs measure the same
+// (1.01 TB/s), 8 CTAs (63 registers) is 11 % slower (profiles/r01_quick_bench_v3.txt).  MXD_TUNE_MINB=8 keeps the
+// 8-CTA build selectable for A/B profiling.
+static int g_minb = [] { const char* e = getenv("MXD_TUNE_MINB"); return (e && atoi(e) == 8) ? 8 : 6; }();
 
 cudaError_t launch_sha256(const MsgJob& job, cudaStream_t stream) {
     if (job.nmsg == 0) return cudaSuccess;
     const uint64_t blocks = (job.nmsg + kThreads - 1) / kThreads;
     if (blocks > 0x7fffffffull) return cudaErrorInvalidValue;
-    if (g_minb == 6) k_sha256_lanes<6><<<(unsigned)blocks, kThreads, 0, stream>>>(job);
-    else             k_sha256_lanes<8><<<(unsigned)blocks, kThreads, 0, stream>>>(job);
+    if (g_minb == 8) k_sha256_lanes<8><<<(unsigned)blocks, kThreads, 0, stream>>>(job);
+    else             k_sha256_lanes<6><<<(unsigned)blocks, kThreads, 0, stream>>>(job);
     return cudaGetLastError();
 }
 
@@ -237,7 +244,7 @@ cudaError_t launch_tree_root(uint64_t size, uint64_t leaf, uint32_t fanout, cons
 
 int sha256_kernel_regs() {
     cudaFuncAttributes a;
-    if (cudaFuncGetAttributes(&a, g_minb == 6 ? k_sha256_lanes<6> : k_sha256_lanes<8>) != cudaSuccess) return -1;
+    if (cudaFuncGetAttributes(&a, k_sha256_lanes<6>) != cudaSuccess) return -1;
     return a.numRegs;
 }
 

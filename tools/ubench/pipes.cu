@@ -17,13 +17,14 @@ constexpr int CHAINS = 8;      // independent dependency chains per thread (cove
 constexpr int INNER  = 32;     // unrolled ops per chain per loop trip
 
 enum Mix { SHF = 0, LOP3, IADD3, IMADADD, IMADWIDE, IMADSHL, SHF_IMAD, LOP3_IMAD, SHF_LOP3, SHF_IMADWIDE,
-           SHA_MIX, PRMT, IMADWIDE_IMM, SHF_IMAD_IMAD, NMIX };
+           SHA_MIX, PRMT, IMADWIDE_IMM, SHF_IMAD_IMAD, IMADHI, IMADHI_LOP3, IMADHI_SHF_LOP3, ROT_FMA_LOP3, NMIX };
 static const char* mix_name[NMIX] = {
   "SHF.R.W (rotate)", "LOP3 (xor3)", "IADD3", "IMAD (x*1+y, fma pipe)", "1 IMAD.WIDE.U32 (x*reg) : 1 LOP3",
   "IMAD.SHL (x*2^k imm)", "1 SHF : 1 IMAD", "1 LOP3 : 1 IMAD", "1 SHF : 1 LOP3", "1 SHF : 1 IMAD.WIDE : 1 LOP3",
-  "sha-like 6 SHF : 3 LOP3 : 2 IADD3 : 1 IMAD", "PRMT", "1 IMAD.WIDE.U32 (x*imm) : 1 LOP3", "1 SHF : 2 IMAD" };
+  "sha-like 6 SHF : 3 LOP3 : 2 IADD3 : 1 IMAD", "PRMT", "1 IMAD.WIDE.U32 (x*imm) : 1 LOP3", "1 SHF : 2 IMAD",
+  "IMAD.HI.U32 (x*reg hi)", "1 IMAD.HI.U32 : 1 LOP3", "1 IMAD.HI : 1 SHF : 1 LOP3", "rot via IMAD.HI+IMAD : 1 LOP3 (2 fma : 1 alu)" };
 // instructions issued per "op slot" of the inner loop, for rate accounting
-static const int mix_instr[NMIX] = {1, 1, 1, 1, 2, 1, 2, 2, 2, 3, 12, 1, 2, 3};
+static const int mix_instr[NMIX] = {1, 1, 1, 1, 2, 1, 2, 2, 2, 3, 12, 1, 2, 3, 1, 2, 3, 3};
 
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 template <int MIX>
@@ -78,6 +79,22 @@ __global__ void __launch_bounds__(256) k_pipe(uint32_t* out, int iters, uint32_t
           asm volatile("shf.r.wrap.b32 %0, %0, %0, 7;" : "+r"(x[c]));
           asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(w) : "r"(y[c]), "r"(mulc));
           y[c] = (uint32_t)w ^ (uint32_t)(w >> 32);   // one extra LOP3 (counted as part of the 2; slight under-count)
+        } else if (MIX == IMADHI) {
+          asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(x[c]) : "r"(mulc));
+          asm volatile("" : "+r"(x[c]));
+        } else if (MIX == IMADHI_LOP3) {
+          asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(y[c]) : "r"(x[c]), "r"(mulc));
+          asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[c]) : "r"(y[c]), "r"(one));
+        } else if (MIX == IMADHI_SHF_LOP3) {
+          uint32_t t;
+          asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(t) : "r"(x[c]), "r"(mulc));
+          asm volatile("shf.r.wrap.b32 %0, %0, %0, 7;" : "+r"(y[c]));
+          asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[c]) : "r"(y[c]), "r"(t));
+        } else if (MIX == ROT_FMA_LOP3) {
+          uint32_t t;
+          asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(t) : "r"(x[c]), "r"(mulc));          // x >> 6
+          asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(t) : "r"(x[c]), "r"(mulc));      // + x << 26  => rotr(x, 6)
+          asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[c]) : "r"(y[c]), "r"(t));
         } else if (MIX == SHA_MIX) {
           uint32_t a, b, d;
           asm volatile("shf.r.wrap.b32 %0, %1, %1, 6;"  : "=r"(a) : "r"(x[c]));
@@ -141,7 +158,7 @@ int main() {
   CK(cudaMalloc(&out, sizeof(uint32_t) * 148 * 2048 * 2)); CK(cudaMalloc(&cyc, sizeof(long long) * 8192));
   k_pipe<SHA_MIX><<<148 * 2, 256>>>(out, 20000, 1u, 3u, cyc); CK(cudaDeviceSynchronize());  // clock warm-up
   const int nsm = p.multiProcessorCount;
-  for (int w : {8, 16, 32, 48}) {
+  for (int w : {16, 32}) {
     run<SHF>(nsm, w, out, cyc, p.clockRate);
     run<LOP3>(nsm, w, out, cyc, p.clockRate);
     run<IADD3>(nsm, w, out, cyc, p.clockRate);
@@ -156,6 +173,10 @@ int main() {
     run<SHF_LOP3>(nsm, w, out, cyc, p.clockRate);
     run<SHF_IMADWIDE>(nsm, w, out, cyc, p.clockRate);
     run<SHA_MIX>(nsm, w, out, cyc, p.clockRate);
+    run<IMADHI>(nsm, w, out, cyc, p.clockRate);
+    run<IMADHI_LOP3>(nsm, w, out, cyc, p.clockRate);
+    run<IMADHI_SHF_LOP3>(nsm, w, out, cyc, p.clockRate);
+    run<ROT_FMA_LOP3>(nsm, w, out, cyc, p.clockRate);
     printf("\n");
   }
   return 0;
