@@ -90,6 +90,28 @@ PROTOTYPES = {
     "mxd_dev_gen_fill": (C.c_int, [vp, C.c_int, vp, C.c_uint64, C.c_uint64, C.c_uint64, vp]),
 }
 
+cpp = C.POINTER(C.c_char_p)
+# host-side mirror of pkg/client / pkg/registry (include/modelx_client.h)
+PROTOTYPES.update({
+    "mxc_last_error": (C.c_char_p, []),
+    "mxc_free": (None, [C.c_void_p]),
+    "mxc_parse_manifest": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "mxc_push_digest": (C.c_int, [vp, C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "mxc_pull_check": (C.c_int, [vp, C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "mxc_fs_put_blob": (C.c_int, [vp, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]),
+    "mxc_fs_exists_blob": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p]),
+    "mxc_fs_put_manifest": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p]),
+    "mxc_fs_get_manifest": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "mxc_blob_digest_path": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "mxc_push_local": (C.c_int, [vp, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "mxc_pull_local": (C.c_int, [vp, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p)]),
+})
+
+MXC_ERR_DIGEST_INVALID = -20
+MXC_ERR_UNSUPPORTED = -21
+MXC_ERR_MANIFEST = -22
+MXC_ERR_NOT_FOUND = -23
+
 _lib = None
 
 
@@ -114,9 +136,13 @@ def load() -> C.CDLL:
 class MxdError(RuntimeError):
     def __init__(self, status: int, where: str):
         lib = load()
-        detail = lib.mxd_last_error().decode(errors="replace")
+        if where.startswith("mxc_"):
+            detail = lib.mxc_last_error().decode(errors="replace")
+        else:
+            detail = lib.mxd_last_error().decode(errors="replace")
         super().__init__(f"{where}: {lib.mxd_strerror(status).decode()} ({status}) {detail}")
         self.status = status
+        self.detail = detail
 
 
 def check(status: int, where: str) -> None:
