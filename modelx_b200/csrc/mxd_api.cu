@@ -469,25 +469,32 @@ int lockstep_digest(mxd_ctx* c, DevState* d, const LockstepInput& in, uint8_t* o
         auto* prefix = reinterpret_cast<uint64_t*>(hd + n * sizeof(mxd::DevSpan));
         uint8_t* ctl = hd + n * (sizeof(mxd::DevSpan) + sizeof(uint64_t));
         uint64_t moved = 0;
-        for (uint64_t i = 0; i < n && rc == MXD_OK; ++i) {
+        struct Fill { uint64_t i, done, take; };
+        std::vector<Fill> fills;
+        for (uint64_t i = 0; i < n; ++i) {
             // message i ends in round k_fin; it is finalised there and skipped afterwards
             const uint64_t L = in.len[i];
             const uint64_t k_fin = L ? (L - 1) / S : 0;
             if (k > k_fin) { spans[i] = {d_slot, 0}; prefix[i] = L; ctl[i] = 2; continue; }
             const uint64_t done = k * S;
             const uint64_t take = std::min(L - done, S);
-            const bool last = (k == k_fin);
-            const uint8_t* from = nullptr;
-            if (take) {
-                Source one = in.src[i];
-                one.pinned = false;  // gather into the slot so the whole round is one H2D copy
-                rc = source_stage(one, done, take, h_slot + i * S, &from);
-            }
             spans[i] = {d_slot + i * S, take};
             prefix[i] = done;
-            ctl[i] = last ? 1 : 0;
+            ctl[i] = (k == k_fin) ? 1 : 0;
             moved += take;
+            if (take) fills.push_back({i, done, take});
         }
+        // gather this round's bytes of every running message into the slot, files read in parallel
+        std::vector<int> frc(fills.size(), MXD_OK);
+        std::vector<std::string> ferr(fills.size());
+        d->pool->parallel_for((int)fills.size(), [&](int f) {
+            Source one = in.src[fills[f].i];
+            one.pinned = false;   // always copy into the slot so the whole round is one H2D transfer
+            const uint8_t* from = nullptr;
+            frc[f] = source_stage(one, fills[f].done, fills[f].take, h_slot + fills[f].i * S, &from);
+            if (frc[f] != MXD_OK) ferr[f] = g_last_error;
+        });
+        for (size_t f = 0; f < fills.size(); ++f) if (frc[f] != MXD_OK) { rc = fail(frc[f], ferr[f]); break; }
         if (rc != MXD_OK) break;
         const uint64_t span_bytes = n * S;
         e = cudaMemcpyAsync(d_slot, h_slot, span_bytes, cudaMemcpyHostToDevice, d->copy);

@@ -152,6 +152,169 @@ __global__ void __launch_bounds__(kThreads, MINB) k_sha256_lanes(const MsgJob j)
 }
 
 
+
+// =====================================================================================================
+// k_sha256_chains_coop: few, long chains.  A SHA-256 chain is serial, so when a launch has only a few
+// thousand messages (a push/pull of a few hundred files, one streamed file, a ring slot) the lanes
+// kernel above is latency bound: a lone warp needs ~3,300 clk per block because the 480-instruction
+// message schedule and the loads sit in the same instruction stream as the 64 dependent rounds.
+// Here every 32 chains get two warps on two different SM sub-partitions:
+//   warp 1 (producer)  loads/pads block b of its 32 messages, expands the schedule and stores
+//                      W[t]+K[t] (t = 0..63) to shared memory, one stage ahead;
+//   warp 0 (chain)     runs only the 64 rounds, reading W[t]+K[t] with LDS.128 (16 per block).
+// The chain warp's critical path is then ~18 clk per round.  Same MsgJob contract as the lanes kernel
+// (spans or segments, chained state, per-message control bytes), same results bit for bit.
+// =====================================================================================================
+constexpr int kCoopStages = 2;
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(nthreads) : "memory"); }
+
+__global__ void __launch_bounds__(64) k_sha256_chains_coop(const MsgJob j) {
+    // wk[stage][t/4][lane] = {W+K for rounds 4g..4g+3} of that lane's current block
+    __shared__ uint4 wk[kCoopStages][16][32];
+    const int lane = threadIdx.x & 31;
+    const int role = threadIdx.x >> 5;            // 0 = chain warp, 1 = producer warp
+    const uint64_t m = (uint64_t)blockIdx.x * 32 + lane;
+    const bool valid = m < j.nmsg;
+    const uint32_t one = j.one;
+
+    const uint8_t* ptr = nullptr;
+    uint64_t len = 0;
+    if (valid) {
+        if (j.base != nullptr) {
+            const uint64_t off = m * j.seg;
+            ptr = j.base + off;
+            len = (off < j.nbytes) ? ((j.nbytes - off < j.seg) ? j.nbytes - off : j.seg) : 0;
+        } else {
+            const DevSpan sp = reinterpret_cast<const DevSpan*>(j.spans)[m];
+            ptr = static_cast<const uint8_t*>(sp.ptr);
+            len = sp.len;
+        }
+    }
+    const uint64_t prefix = (j.prefix != nullptr && valid) ? j.prefix[m] : j.prefix_all;
+    const uint64_t nfull = len >> 6;
+    const uint32_t r = (uint32_t)(len & 63u);
+    int fin = j.finalize;
+    bool live = valid;
+    if (j.ctl != nullptr && valid) { const uint8_t c = j.ctl[m]; fin = (c == 1); live = (c != 2); }
+    const uint64_t nblk = live ? nfull + (fin ? (r >= 56 ? 2u : 1u) : 0u) : 0;
+    const uint64_t bits = (prefix + len) << 3;
+    // both warps iterate to the longest chain of the 32; shorter lanes idle through the barriers
+    uint64_t nmax = nblk;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const uint64_t other = __shfl_xor_sync(0xffffffffu, nmax, o); nmax = other > nmax ? other : nmax; }
+
+    constexpr int kFull0 = 1, kEmpty0 = 1 + kCoopStages;   // named barrier ids (0 is __syncthreads)
+
+    if (role == 1) {
+        // ---------------- producer: load / pad, expand, publish W+K ---------------------------------
+        constexpr K256Table K = k256_table();
+        const bool warp_aligned = __all_sync(0xffffffffu, (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0);
+        uint32_t w[16];
+        for (uint64_t b = 0; b < nmax; ++b) {
+            const int st = (int)(b % kCoopStages);
+            if (b >= (uint64_t)kCoopStages) named_bar_sync(kEmpty0 + st, 64);   // chain warp has drained this stage
+            if (b < nblk) {
+                if (b < nfull) {
+                    if (warp_aligned) {
+                        const uint4* p4 = reinterpret_cast<const uint4*>(ptr + (b << 6));
+                        const uint4 v0 = ldg128(p4), v1 = ldg128(p4 + 1), v2 = ldg128(p4 + 2), v3 = ldg128(p4 + 3);
+                        unpack_block(v0, v1, v2, v3, w);
+                    } else {
+                        load_block_unaligned(ptr + (b << 6), w);
+                    }
+                } else if (b == nfull) {
+                    const uint8_t* t = ptr + (nfull << 6);
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        uint32_t word = 0;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const uint32_t idx = 4 * k + q;
+                            if (idx < r) word |= (uint32_t)__ldg(t + idx) << (24 - 8 * q);
+                            else if (idx == r) word |= 0x80u << (24 - 8 * q);
+                        }
+                        w[k] = word;
+                    }
+                    if (r < 56) { w[14] = (uint32_t)(bits >> 32); w[15] = (uint32_t)bits; }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 14; ++k) w[k] = 0;
+                    w[14] = (uint32_t)(bits >> 32); w[15] = (uint32_t)bits;
+                }
+#pragma unroll
+                for (int g = 0; g < 16; ++g) {
+                    uint32_t o4[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int t = 4 * g + q;
+                        if (t >= 16) {
+                            uint32_t x = add_fma(w[t & 15], small_sigma0(w[(t + 1) & 15]), one);
+                            x = add_fma(x, w[(t + 9) & 15], one);
+                            w[t & 15] = add_fma(x, small_sigma1(w[(t + 14) & 15]), one);
+                        }
+                        o4[q] = add_fma(w[t & 15], K.v[t], one);
+                    }
+                    wk[st][g][lane] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+                }
+            }
+            named_bar_arrive(kFull0 + st, 64);
+        }
+        return;
+    }
+
+    // ---------------- chain warp: 64 rounds per block on W+K from shared memory ------------------------
+    uint32_t h[8];
+    if (valid && j.state != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) h[i] = j.state[8 * m + i];
+    } else {
+        sha256_iv(h);
+    }
+    for (uint64_t b = 0; b < nmax; ++b) {
+        const int st = (int)(b % kCoopStages);
+        named_bar_sync(kFull0 + st, 64);
+        if (b < nblk) {
+            uint32_t s[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s[i] = h[i];
+#pragma unroll
+            for (int g = 0; g < 16; ++g) {
+                const uint4 v = wk[st][g][lane];
+                const uint32_t wkq[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int t = 4 * g + q;
+                    uint32_t& a = s[(0 - t) & 7]; uint32_t& bb = s[(1 - t) & 7]; uint32_t& c = s[(2 - t) & 7];
+                    uint32_t& d = s[(3 - t) & 7]; uint32_t& e = s[(4 - t) & 7]; uint32_t& f = s[(5 - t) & 7];
+                    uint32_t& gg = s[(6 - t) & 7]; uint32_t& hh = s[(7 - t) & 7];
+                    uint32_t t1 = add_fma(wkq[q], hh, one);
+                    t1 = add_fma(t1, ch(e, f, gg), one);
+                    t1 = add_fma(t1, big_sigma1(e), one);
+                    d = add_fma(d, t1, one);
+                    const uint32_t t2 = add_fma(big_sigma0(a), maj(a, bb, c), one);
+                    hh = add_fma(t1, t2, one);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) h[i] = add_fma(h[i], s[i], one);
+        }
+        if (b + kCoopStages < nmax) named_bar_arrive(kEmpty0 + st, 64);
+    }
+    if (!live) return;
+    if (!fin) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) j.state[8 * m + i] = h[i];
+        return;
+    }
+    uint4 lo, hi;
+    lo.x = bswap32(h[0]); lo.y = bswap32(h[1]); lo.z = bswap32(h[2]); lo.w = bswap32(h[3]);
+    hi.x = bswap32(h[4]); hi.y = bswap32(h[5]); hi.z = bswap32(h[6]); hi.w = bswap32(h[7]);
+    uint4* o = reinterpret_cast<uint4*>(j.out + 32 * m);
+    o[0] = lo; o[1] = hi;
+}
+
 // One thread: the 72-byte root message of modelx.tree.v1 (two blocks with padding).
 __global__ void k_tree_root(uint64_t size, uint64_t leaf, uint32_t fanout, const uint8_t* __restrict__ top,
                             uint8_t* __restrict__ root, uint32_t one) {
@@ -211,10 +374,19 @@ __global__ void k_gen_fill(uint64_t* __restrict__ dst, uint64_t first_word, uint
 // 8-CTA build selectable for A/B profiling.
 static int g_minb = [] { const char* e = getenv("MXD_TUNE_MINB"); return (e && atoi(e) == 8) ? 8 : 6; }();
 
+static long g_coop_max = [] { const char* e = getenv("MXD_TUNE_COOP"); return e ? atol(e) : 8192L; }();
+
 cudaError_t launch_sha256(const MsgJob& job, cudaStream_t stream) {
     if (job.nmsg == 0) return cudaSuccess;
     const uint64_t blocks = (job.nmsg + kThreads - 1) / kThreads;
     if (blocks > 0x7fffffffull) return cudaErrorInvalidValue;
+    // Few, long chains: two warps per 32 chains (see k_sha256_chains_coop).  Above ~8k chains the lanes kernel
+    // already keeps the ALU pipe busy and is the better choice.  MXD_TUNE_COOP=0 disables, =N sets the threshold.
+    if (job.nmsg <= (uint64_t)g_coop_max) {
+        const uint64_t cblocks = (job.nmsg + 31) / 32;
+        k_sha256_chains_coop<<<(unsigned)cblocks, 64, 0, stream>>>(job);
+        return cudaGetLastError();
+    }
     if (g_minb == 8) k_sha256_lanes<8><<<(unsigned)blocks, kThreads, 0, stream>>>(job);
     else             k_sha256_lanes<6><<<(unsigned)blocks, kThreads, 0, stream>>>(job);
     return cudaGetLastError();
