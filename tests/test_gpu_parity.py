@@ -306,3 +306,34 @@ def test_cancel(oracle):
         assert ei.value.status == -6
         eng.reset_cancel()
         assert eng.tree_digest(blob, 1 << 20, 16 << 10, 8)[1] == oracle.tree_digest(blob, 1 << 20, 16 << 10, 8)[2]
+
+
+# ------------------------------------------------------------------------------------------------
+# one process driving several GPUs (mxd_open with a device list): chunk ranges per device
+# ------------------------------------------------------------------------------------------------
+def test_in_process_multi_gpu_tree_digest(oracle, tmp_path):
+    torch = _torch()
+    ndev = torch.cuda.device_count()
+    if ndev < 2:
+        pytest.skip("needs >= 2 GPUs in one box")
+    size = 200_000_000 + 12345
+    blob = oracle.gen(0, size, SEED + 20)
+    want_chunks, _, want_root = oracle.tree_digest(blob, 8 << 20, 16 << 10, 8)
+    p = tmp_path / "blob.bin"
+    p.write_bytes(blob)
+    with modelx_b200.Engine(devices=list(range(ndev))) as eng:
+        assert eng.device_count() == ndev
+        chunks, root = eng.tree_digest(blob)                       # pageable host memory, split across devices
+        assert (chunks, root) == (want_chunks, want_root)
+        chunks, root, sz = eng.tree_digest_file(str(p))            # file, split across devices
+        assert (chunks, root, sz) == (want_chunks, want_root, size)
+        # whole-file digests are spread round-robin over the devices
+        paths = []
+        for i in range(2 * ndev):
+            q = tmp_path / f"f{i}"
+            q.write_bytes(blob[i * 1000:i * 1000 + 3_000_000 + i])
+            paths.append(str(q))
+        got, _ = eng.sha256_files(paths)
+        assert got == [hashlib.sha256(blob[i * 1000:i * 1000 + 3_000_000 + i]).digest() for i in range(2 * ndev)]
+        for pth in paths[:ndev + 1]:
+            assert eng.sha256_file(pth)[0] == hashlib.sha256(open(pth, "rb").read()).digest()
