@@ -337,3 +337,32 @@ def test_in_process_multi_gpu_tree_digest(oracle, tmp_path):
         assert got == [hashlib.sha256(blob[i * 1000:i * 1000 + 3_000_000 + i]).digest() for i in range(2 * ndev)]
         for pth in paths[:ndev + 1]:
             assert eng.sha256_file(pth)[0] == hashlib.sha256(open(pth, "rb").read()).digest()
+
+
+def test_cancel_from_another_thread_mid_stream(oracle):
+    """ctx cancel while a large pageable blob is streaming: the call returns MXD_ERR_CANCELED promptly
+    (push.go:156-159 semantics) and the engine is usable again after reset."""
+    import numpy as np
+    size = 3_000_000_000
+    blob = np.zeros(size, dtype=np.uint8)
+    blob[::4096] = 7
+    with modelx_b200.Engine(devices=[0], ring_bytes=64 << 20) as eng:
+        result = {}
+
+        def work():
+            try:
+                eng.tree_digest_ptr(blob.ctypes.data, size)
+                result["rc"] = 0
+            except modelx_b200.MxdError as e:
+                result["rc"] = e.status
+
+        t = threading.Thread(target=work)
+        t.start()
+        import time
+        time.sleep(0.05)
+        eng.cancel()
+        t.join(timeout=60)
+        assert not t.is_alive() and result["rc"] == -6
+        eng.reset_cancel()
+        small = oracle.gen(0, 5_000_000, SEED)
+        assert eng.tree_digest(small)[1] == oracle.tree_digest(small, 8 << 20, 16 << 10, 8)[2]
