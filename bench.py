@@ -367,7 +367,7 @@ def run_b200(args):
             cpu = {"value": sample / dt1 / GB, "unit": "GB/s", "cores": 1, "kind": "port",
                    "sample": f"first {sample/1e9:g} GB of the blob, one SHA-256 chain on one thread (what the reference does "
                              "for one blob, push.go:149-161), SHA-NI, data already in memory (no read syscalls)",
-                   "engine": "sha-ni" if orc.engine() == 1 else "portable", "host_cpus": threads,
+                   "engine": "sha-ni" if orc.engine() == 1 else "portable", "host_cpus": os.cpu_count(),
                    "all_cores_tree": {"value": my_bytes / dtn / GB, "unit": "GB/s", "cores": threads,
                                       "sample": "the whole blob, same tree digest chunk-parallel on host threads (32: the "
                                                 "measured plateau, more threads are slower on this box)",

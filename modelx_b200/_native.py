@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmodelxdigest.so")
+# MODELX_B200_LIB lets a developer A/B an experimental build of the same library; default is the in-tree build.
+LIB_PATH = os.environ.get("MODELX_B200_LIB") or os.path.join(_HERE, "libmodelxdigest.so")
 
 MXD_OK = 0
 MXD_ERR_INVALID = -1
