@@ -149,8 +149,6 @@ struct DevState {
     uint8_t* h_ring = nullptr;  // kSlots * slot_bytes, pinned
     uint8_t* d_ring = nullptr;  // kSlots * slot_bytes
     cudaEvent_t ev_copied[kSlots] = {}, ev_done[kSlots] = {};
-    uint8_t* h_small = nullptr;  // pinned scratch for small results / descriptors
-    uint64_t h_small_bytes = 0;
     std::mutex mu;               // one streaming operation per device at a time
     StagePool* pool = nullptr;   // slot fillers for this device
 };
@@ -674,8 +672,6 @@ int mxd_open(mxd_ctx** out, const int* devices, int ndev, uint64_t ring_bytes) {
         if ((e = cudaStreamCreateWithFlags(&d->copy, cudaStreamNonBlocking)) != cudaSuccess) break;
         if ((e = cudaHostAlloc(&d->h_ring, slot * kSlots, cudaHostAllocPortable)) != cudaSuccess) break;
         if ((e = cudaMalloc(&d->d_ring, slot * kSlots)) != cudaSuccess) break;
-        d->h_small_bytes = 1 << 20;
-        if ((e = cudaHostAlloc(&d->h_small, d->h_small_bytes, cudaHostAllocPortable)) != cudaSuccess) break;
         for (int s = 0; s < kSlots && e == cudaSuccess; ++s) {
             e = cudaEventCreateWithFlags(&d->ev_copied[s], cudaEventDisableTiming);
             if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_done[s], cudaEventDisableTiming);
@@ -711,7 +707,6 @@ void mxd_close(mxd_ctx* c) {
         }
         if (d->h_ring) cudaFreeHost(d->h_ring);
         if (d->d_ring) cudaFree(d->d_ring);
-        if (d->h_small) cudaFreeHost(d->h_small);
         delete d->pool;
         delete d;
     }
