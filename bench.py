@@ -357,6 +357,9 @@ def run_b200(args):
             t0 = time.perf_counter()
             d_one = orc.sha256_ptr(host_ptr, sample)                 # reference semantics: one serial chain, 1 thread
             dt1 = time.perf_counter() - t0
+            t0 = time.perf_counter()                                   # the reference's PullPushConcurrency = 3 (push.go:27)
+            orc.tree_digest_ptr(host_ptr, sample, *tp, threads=3)
+            dt3 = time.perf_counter() - t0
             threads = min(os.cpu_count() or 1, 32)   # plateaus at 16-32 threads on the bench box (profiles/r01_cpu_scaling.txt)
             t0 = time.perf_counter()
             want_chunks, _, want_root = orc.tree_digest_ptr(host_ptr, my_bytes, *tp, threads=threads)
@@ -368,6 +371,8 @@ def run_b200(args):
                    "sample": f"first {sample/1e9:g} GB of the blob, one SHA-256 chain on one thread (what the reference does "
                              "for one blob, push.go:149-161), SHA-NI, data already in memory (no read syscalls)",
                    "engine": "sha-ni" if orc.engine() == 1 else "portable", "host_cpus": os.cpu_count(),
+                   "three_threads_tree": {"value": sample / dt3 / GB, "unit": "GB/s", "cores": 3,
+                                          "sample": f"first {sample/1e9:g} GB, tree digest on 3 threads (the reference's PullPushConcurrency)"},
                    "all_cores_tree": {"value": my_bytes / dtn / GB, "unit": "GB/s", "cores": threads,
                                       "sample": "the whole blob, same tree digest chunk-parallel on host threads (32: the "
                                                 "measured plateau, more threads are slower on this box)",

@@ -6,6 +6,7 @@
 #include "../../include/modelx_digest.h"
 #include "kernels.h"
 
+#include <algorithm>
 #include <atomic>
 #include <cerrno>
 #include <condition_variable>
@@ -566,6 +567,37 @@ int lockstep_digest(mxd_ctx* c, DevState* d, const LockstepInput& in, uint8_t* o
     return rc;
 }
 
+// Spread a batch of whole messages over every device of the context (largest first onto the least
+// loaded device), one lock-step batch per device running concurrently; results keep the caller's order.
+int lockstep_digest_all(mxd_ctx* c, const LockstepInput& in, uint8_t* out) {
+    const uint64_t n = in.src.size();
+    const size_t G = std::min<uint64_t>(c->devs.size(), std::max<uint64_t>(n, 1));
+    if (G <= 1) return lockstep_digest(c, pick_device(c), in, out);
+    std::vector<uint64_t> order(n);
+    for (uint64_t i = 0; i < n; ++i) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) { return in.len[a] > in.len[b]; });
+    std::vector<std::vector<uint64_t>> group(G);
+    std::vector<uint64_t> load(G, 0);
+    for (uint64_t idx : order) {
+        size_t g = (size_t)(std::min_element(load.begin(), load.end()) - load.begin());
+        group[g].push_back(idx); load[g] += in.len[idx] + 1;
+    }
+    std::vector<int> rcs(G, MXD_OK);
+    std::vector<std::string> errs(G);
+    std::vector<std::thread> th;
+    for (size_t g = 0; g < G; ++g) th.emplace_back([&, g] {
+        LockstepInput part;
+        for (uint64_t idx : group[g]) { part.src.push_back(in.src[idx]); part.len.push_back(in.len[idx]); }
+        std::vector<uint8_t> o(32 * part.src.size());
+        rcs[g] = lockstep_digest(c, c->devs[g], part, o.data());
+        if (rcs[g] != MXD_OK) { errs[g] = g_last_error; return; }
+        for (size_t k = 0; k < group[g].size(); ++k) memcpy(out + 32 * group[g][k], &o[32 * k], 32);
+    });
+    for (auto& t : th) t.join();
+    for (size_t g = 0; g < G; ++g) if (rcs[g] != MXD_OK) return fail(rcs[g], errs[g]);
+    return MXD_OK;
+}
+
 int open_files(const char* const* paths, uint64_t n, LockstepInput* in, std::vector<int>* fds) {
     in->src.resize(n); in->len.resize(n);
     for (uint64_t i = 0; i < n; ++i) {
@@ -974,7 +1006,7 @@ int mxd_sha256_batch(mxd_ctx* c, const mxd_span* spans, uint64_t n, uint8_t* out
     LockstepInput in;
     in.src.resize(n); in.len.resize(n);
     for (uint64_t i = 0; i < n; ++i) { in.src[i].mem = static_cast<const uint8_t*>(spans[i].ptr); in.len[i] = spans[i].len; }
-    return lockstep_digest(c, pick_device(c), in, out);
+    return lockstep_digest_all(c, in, out);
 }
 
 int mxd_sha256(mxd_ctx* c, const void* data, uint64_t n, uint8_t out[32]) {
@@ -990,7 +1022,7 @@ int mxd_sha256_files(mxd_ctx* c, const char* const* paths, uint64_t n, uint8_t* 
     int rc = open_files(paths, n, &in, &fds);
     if (rc != MXD_OK) return rc;
     if (sizes) for (uint64_t i = 0; i < n; ++i) sizes[i] = in.len[i];
-    rc = lockstep_digest(c, pick_device(c), in, out);
+    rc = lockstep_digest_all(c, in, out);
     for (int fd : fds) close(fd);
     return rc;
 }
