@@ -201,7 +201,8 @@ bool tree_resolve(const mxd_tree_params* tp, Tree* t) {
 int enqueue_segments(mxd_ctx* c, const uint8_t* d_data, uint64_t nbytes, uint64_t seg, uint8_t* d_out, cudaStream_t st,
                      bool leaf_level = false) {
     mxd_ctx::ProfRec rec{};
-    const bool prof = leaf_level && c->prof_on.load();
+    bool prof = leaf_level && c->prof_on.load();
+    if (prof) { std::lock_guard<std::mutex> lk(c->prof_mu); if (c->prof.size() >= (1u << 16)) prof = false; }   // bounded
     if (prof) {
         cudaGetDevice(&rec.ordinal);
         MXD_CUDA(cudaEventCreate(&rec.a));
@@ -385,6 +386,7 @@ int stream_tree_chunks(mxd_ctx* c, DevState* d, const Tree& t, const Source& src
     MXD_CUDA(cudaMalloc(&d_leaves, n0 * 32));
     int rc = stream_segments(c, d, src, nbytes, t.leaf, d_leaves);
     if (rc == MXD_OK) rc = enqueue_leaves_to_chunks(c, t, d_leaves, n0, d_chunks, d->compute);
+    if (rc != MXD_OK) cudaStreamSynchronize(d->copy);   // nothing may still be reading the caller's (pinned) memory
     cudaError_t e = cudaStreamSynchronize(d->compute);
     if (rc == MXD_OK && e != cudaSuccess) rc = fail(MXD_ERR_CUDA, std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e));
     cudaFree(d_leaves);
@@ -473,12 +475,13 @@ int lockstep_digest(mxd_ctx* c, DevState* d, const LockstepInput& in, uint8_t* o
     if (n == 0) return MXD_OK;
     std::lock_guard<std::mutex> lk(d->mu);
     DeviceGuard guard(d->ordinal);
-    uint64_t S = (d->slot_bytes / n) & ~63ull;
-    if (S == 0) return fail(MXD_ERR_INVALID, "too many messages for the ring slot; raise ring_bytes or split the batch");
-    if (S > (8ull << 20)) S = 8ull << 20;
-    uint64_t maxlen = 0;
-    for (uint64_t i = 0; i < n; ++i) maxlen = std::max(maxlen, in.len[i]);
-    const uint64_t rounds = std::max<uint64_t>(1, (maxlen + S - 1) / S);
+    if ((d->slot_bytes / n) < 64) return fail(MXD_ERR_INVALID, "too many messages for the ring slot; raise ring_bytes or split the batch");
+    // Per round every still-running message advances by S bytes, S = slot / (running messages) rounded down to
+    // 64 and capped at 8 MiB; finished messages give their share of the slot to the rest, and only the
+    // occupied part of the slot is copied.
+    std::vector<uint64_t> done(n, 0);
+    std::vector<uint8_t> finished(n, 0);
+    uint64_t running = n;
 
     // per-round descriptors live in pinned memory, double-buffered per slot
     const uint64_t desc_bytes = (n * (sizeof(mxd::DevSpan) + sizeof(uint64_t) + 1) + 255) & ~255ull;
@@ -497,7 +500,7 @@ int lockstep_digest(mxd_ctx* c, DevState* d, const LockstepInput& in, uint8_t* o
         e = cudaMemcpy(d_state, iv.data(), n * 32, cudaMemcpyHostToDevice);
         if (e != cudaSuccess) rc = fail(MXD_ERR_CUDA, cudaGetErrorString(e));
     }
-    for (uint64_t k = 0; k < rounds && rc == MXD_OK; ++k) {
+    for (uint64_t k = 0; running > 0 && rc == MXD_OK; ++k) {
         if (c->canceled.load()) { rc = fail(MXD_ERR_CANCELED, "canceled"); break; }
         const int s = (int)(k % kSlots);
         if (k >= (uint64_t)kSlots) {
@@ -510,22 +513,24 @@ int lockstep_digest(mxd_ctx* c, DevState* d, const LockstepInput& in, uint8_t* o
         auto* spans = reinterpret_cast<mxd::DevSpan*>(hd);
         auto* prefix = reinterpret_cast<uint64_t*>(hd + n * sizeof(mxd::DevSpan));
         uint8_t* ctl = hd + n * (sizeof(mxd::DevSpan) + sizeof(uint64_t));
-        uint64_t moved = 0;
-        struct Fill { uint64_t i, done, take; };
+        const uint64_t S = std::min<uint64_t>(8ull << 20, (d->slot_bytes / running) & ~63ull);
+        uint64_t moved = 0, pos = 0;
+        struct Fill { uint64_t i, done, take, pos; };
         std::vector<Fill> fills;
         for (uint64_t i = 0; i < n; ++i) {
-            // message i ends in round k_fin; it is finalised there and skipped afterwards
-            const uint64_t L = in.len[i];
-            const uint64_t k_fin = L ? (L - 1) / S : 0;
-            if (k > k_fin) { spans[i] = {d_slot, 0}; prefix[i] = L; ctl[i] = 2; continue; }
-            const uint64_t done = k * S;
-            const uint64_t take = std::min(L - done, S);
-            spans[i] = {d_slot + i * S, take};
-            prefix[i] = done;
-            ctl[i] = (k == k_fin) ? 1 : 0;
-            moved += take;
-            if (take) fills.push_back({i, done, take});
+            if (finished[i]) { spans[i] = {d_slot, 0}; prefix[i] = in.len[i]; ctl[i] = 2; continue; }
+            const uint64_t take = std::min(in.len[i] - done[i], S);
+            const bool last = done[i] + take == in.len[i];     // finalised in the round that reaches its end
+            spans[i] = {d_slot + pos * S, take};
+            prefix[i] = done[i];
+            ctl[i] = last ? 1 : 0;
+            if (take) { fills.push_back({i, done[i], take, pos}); ++pos; }   // empty messages occupy no slot space
+            moved += take; done[i] += take;
+            if (last) finished[i] = 1;
         }
+        const uint64_t occupied = pos * S;
+        running = 0;
+        for (uint64_t i = 0; i < n; ++i) running += finished[i] ? 0 : 1;
         // gather this round's bytes of every running message into the slot, files read in parallel
         std::vector<int> frc(fills.size(), MXD_OK);
         std::vector<std::string> ferr(fills.size());
@@ -533,13 +538,13 @@ int lockstep_digest(mxd_ctx* c, DevState* d, const LockstepInput& in, uint8_t* o
             Source one = in.src[fills[f].i];
             one.pinned = false;   // always copy into the slot so the whole round is one H2D transfer
             const uint8_t* from = nullptr;
-            frc[f] = source_stage(one, fills[f].done, fills[f].take, h_slot + fills[f].i * S, &from);
+            frc[f] = source_stage(one, fills[f].done, fills[f].take, h_slot + fills[f].pos * S, &from);
             if (frc[f] != MXD_OK) ferr[f] = g_last_error;
         });
         for (size_t f = 0; f < fills.size(); ++f) if (frc[f] != MXD_OK) { rc = fail(frc[f], ferr[f]); break; }
         if (rc != MXD_OK) break;
-        const uint64_t span_bytes = n * S;
-        e = cudaMemcpyAsync(d_slot, h_slot, span_bytes, cudaMemcpyHostToDevice, d->copy);
+        const uint64_t span_bytes = occupied;
+        e = span_bytes ? cudaMemcpyAsync(d_slot, h_slot, span_bytes, cudaMemcpyHostToDevice, d->copy) : cudaSuccess;
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_desc + desc_bytes * s, hd, desc_bytes, cudaMemcpyHostToDevice, d->copy);
         if (e == cudaSuccess) e = cudaEventRecord(d->ev_copied[s], d->copy);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(d->compute, d->ev_copied[s], 0);
