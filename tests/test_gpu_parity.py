@@ -366,3 +366,23 @@ def test_cancel_from_another_thread_mid_stream(oracle):
         eng.reset_cancel()
         small = oracle.gen(0, 5_000_000, SEED)
         assert eng.tree_digest(small)[1] == oracle.tree_digest(small, 8 << 20, 16 << 10, 8)[2]
+
+
+def test_files_with_skewed_sizes(engine, tmp_path):
+    """Many small files, a few empty ones and one large one in the same lock-step batch: finished
+    messages must release their share of the ring and the long one must still come out right."""
+    rng = random.Random(77)
+    sizes = [0, 0, 1, 63, 64, 65, 4096, 100_000, 1_000_000] * 6 + [150_000_000] + [rng.randrange(0, 300_000) for _ in range(60)]
+    rng.shuffle(sizes)
+    paths, want = [], []
+    for i, n in enumerate(sizes):
+        p = tmp_path / f"s{i}"
+        data = rng.randbytes(n)
+        p.write_bytes(data)
+        paths.append(str(p))
+        want.append(hashlib.sha256(data).digest())
+    got, got_sizes = engine.sha256_files(paths)
+    assert got == want and got_sizes == sizes
+    with modelx_b200.Engine(devices=[0], ring_bytes=4 << 20) as small:       # 1 MiB slots: many rounds
+        got2, _ = small.sha256_files(paths)
+    assert got2 == want
