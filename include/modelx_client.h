@@ -38,9 +38,14 @@ int mxc_parse_manifest(const char* basedir, const char* configfile, char** manif
 /* The digest phase of Client.Push (push.go:29-52 + pushFile :120-147): ParseManifest, then for
  * every file blob and the config: stat -> Size/Mode/Modified and the whole-file SHA-256 digest,
  * all files hashed as ONE lock-step GPU batch (the reference runs 3 goroutines).
- * with_tree != 0 additionally records the modelx.tree.v1 root and parameters of each blob under
- * Descriptor.Annotations["modelx.tree.v1"].  Directory blobs -> MXC_ERR_UNSUPPORTED. */
-int mxc_push_digest(mxd_ctx* ctx, const char* basedir, const char* configfile, int with_tree, char** manifest_json);
+ * flags: MXC_PUSH_TREE additionally records the modelx.tree.v1 root and parameters of each blob under
+ * Descriptor.Annotations["modelx.tree.v1"]; MXC_PUSH_CACHE (new, opt-in) reuses digests
+ * remembered in <basedir>/.modelx/digests.json for files whose size and mtime (ns) are unchanged, and
+ * updates that file -- the reference re-hashes every blob on every push (push.go:125-131).
+ * Directory blobs -> MXC_ERR_UNSUPPORTED. */
+#define MXC_PUSH_TREE  1
+#define MXC_PUSH_CACHE 2
+int mxc_push_digest(mxd_ctx* ctx, const char* basedir, const char* configfile, int flags, char** manifest_json);
 
 /* The check phase of Client.Pull (pull.go:41-50 + pullFile :111-127) for every blob + config of
  * the manifest: state = "already exists" (local file hashes to desc.Digest), "empty"

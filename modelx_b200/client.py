@@ -72,10 +72,12 @@ class Client:
         self.engine = engine
         self._lib = N.load()
 
-    def push_digest_json(self, basedir: str, configfile: str = "modelx.yaml", with_tree: bool = False) -> str:
+    def push_digest_json(self, basedir: str, configfile: str = "modelx.yaml", with_tree: bool = False,
+                         use_cache: bool = False) -> str:
         out = C.c_void_p()
+        flags = (1 if with_tree else 0) | (2 if use_cache else 0)
         N.check(self._lib.mxc_push_digest(self.engine.handle, basedir.encode(), configfile.encode(),
-                                          1 if with_tree else 0, C.byref(out)), "mxc_push_digest")
+                                          flags, C.byref(out)), "mxc_push_digest")
         return _take(self._lib, out)
 
     def pull_check(self, basedir: str, manifest_json: str) -> list:

@@ -297,9 +297,47 @@ int push_file_fill(const std::string& path, Descriptor* d) {
 
 std::string digest_str(const uint8_t* d) { char s[72]; mxd_digest_string(d, s); return s; }
 
+// ---- opt-in digest cache: <basedir>/.modelx/digests.json = {"<name>":{"size":..,"mtime_ns":..,"digest":".."}} ----
+struct CacheEntry { int64_t size = 0; int64_t mtime_ns = 0; std::string digest; };
+std::string cache_path(const std::string& basedir) { return join(join(basedir, ".modelx"), "digests.json"); }
+int write_file(const std::string& path, const std::string& data, mode_t mode);
+int mkdir_all(const std::string& path, mode_t mode);
+void cache_load(const std::string& basedir, std::map<std::string, CacheEntry>* out) {
+    FILE* f = fopen(cache_path(basedir).c_str(), "rb");
+    if (!f) return;
+    std::string text; char buf[65536]; size_t r;
+    while ((r = fread(buf, 1, sizeof buf, f)) > 0) text.append(buf, r);
+    fclose(f);
+    JParser jp{text.c_str(), text.c_str() + text.size(), ""};
+    JVal root;
+    if (!jp.val(root) || root.kind != JVal::Obj) return;        // unreadable cache = no cache
+    for (auto& kv : root.obj) {
+        CacheEntry e;
+        if (auto* x = kv.second.get("size")) e.size = strtoll(x->str.c_str(), nullptr, 10);
+        if (auto* x = kv.second.get("mtime_ns")) e.mtime_ns = strtoll(x->str.c_str(), nullptr, 10);
+        if (auto* x = kv.second.get("digest")) e.digest = x->str;
+        uint8_t tmp[32];
+        if (mxd_digest_parse(e.digest.c_str(), tmp) == MXD_OK) (*out)[kv.first] = e;
+    }
+}
+void cache_store(const std::string& basedir, const std::map<std::string, CacheEntry>& m) {
+    std::string o = "{";
+    bool first = true;
+    for (auto& kv : m) {
+        if (!first) o += ',';
+        first = false;
+        json_string(o, kv.first);
+        o += ":{\"size\":" + std::to_string(kv.second.size) + ",\"mtime_ns\":" + std::to_string(kv.second.mtime_ns) + ",\"digest\":";
+        json_string(o, kv.second.digest); o += '}';
+    }
+    o += '}';
+    if (mkdir_all(join(basedir, ".modelx"), 0755) == MXD_OK) write_file(cache_path(basedir), o, 0644);   // best effort
+}
+
 // Digest phase of Client.Push, push.go:29-52: every file blob + the config through pushFile's
 // "stat, digest" (push.go:120-142); the digests come from one lock-step GPU batch.
-int push_digest(mxd_ctx* ctx, const std::string& basedir, const std::string& configfile, bool with_tree, Manifest* m) {
+int push_digest(mxd_ctx* ctx, const std::string& basedir, const std::string& configfile, int flags, Manifest* m) {
+    const bool with_tree = (flags & MXC_PUSH_TREE) != 0, use_cache = (flags & MXC_PUSH_CACHE) != 0;
     int rc = parse_manifest(basedir, configfile, m);
     if (rc != MXD_OK) return rc;
     std::vector<Descriptor*> files;
@@ -311,17 +349,35 @@ int push_digest(mxd_ctx* ctx, const std::string& basedir, const std::string& con
     if (m->config.name.empty()) return fail(MXD_ERR_IO, "stat " + join(basedir, configfile) + ": no such file or directory");
     files.push_back(&m->config);
     std::vector<std::string> paths;
-    std::vector<const char*> cpaths;
     for (auto* d : files) paths.push_back(join(basedir, d->name));
-    for (auto& p : paths) cpaths.push_back(p.c_str());
-    std::vector<uint8_t> out(32 * files.size());
-    std::vector<uint64_t> sizes(files.size());
-    rc = mxd_sha256_files(ctx, cpaths.data(), files.size(), out.data(), sizes.data());
-    if (rc != MXD_OK) return fail(rc, std::string("digest: ") + mxd_last_error());
+    std::map<std::string, CacheEntry> cache;
+    if (use_cache) cache_load(basedir, &cache);
+    std::vector<struct stat> sts(files.size());
+    std::vector<size_t> todo;                         // indices that really need hashing
     for (size_t i = 0; i < files.size(); ++i) {
-        if (files[i]->digest.empty()) files[i]->digest = digest_str(&out[32 * i]);
+        if (stat(paths[i].c_str(), &sts[i]) != 0) return fail_errno("stat " + paths[i]);
+        const int64_t mt = (int64_t)sts[i].st_mtim.tv_sec * 1000000000ll + sts[i].st_mtim.tv_nsec;
+        auto it = cache.find(files[i]->name);
+        if (use_cache && it != cache.end() && it->second.size == (int64_t)sts[i].st_size && it->second.mtime_ns == mt)
+            files[i]->digest = it->second.digest;
+        else todo.push_back(i);
+    }
+    if (!todo.empty()) {
+        std::vector<const char*> cpaths;
+        for (size_t i : todo) cpaths.push_back(paths[i].c_str());
+        std::vector<uint8_t> out(32 * todo.size());
+        rc = mxd_sha256_files(ctx, cpaths.data(), todo.size(), out.data(), nullptr);
+        if (rc != MXD_OK) return fail(rc, std::string("digest: ") + mxd_last_error());
+        for (size_t k = 0; k < todo.size(); ++k) files[todo[k]]->digest = digest_str(&out[32 * k]);
+    }
+    for (size_t i = 0; i < files.size(); ++i) {
         rc = push_file_fill(paths[i], files[i]);
         if (rc != MXD_OK) return rc;
+        if (use_cache) {
+            CacheEntry e; e.size = (int64_t)sts[i].st_size;
+            e.mtime_ns = (int64_t)sts[i].st_mtim.tv_sec * 1000000000ll + sts[i].st_mtim.tv_nsec; e.digest = files[i]->digest;
+            cache[files[i]->name] = e;
+        }
         if (with_tree) {
             uint8_t root[32]; uint64_t nch = 0, sz = 0;
             rc = mxd_tree_digest_file(ctx, paths[i].c_str(), nullptr, nullptr, 0, &nch, &sz, root);
@@ -329,6 +385,7 @@ int push_digest(mxd_ctx* ctx, const std::string& basedir, const std::string& con
             files[i]->annotations["modelx.tree.v1"] = digest_str(root) + ";leaf=16384;fanout=8;chunk=8388608;chunks=" + std::to_string(nch);
         }
     }
+    if (use_cache) cache_store(basedir, cache);
     return MXD_OK;
 }
 
@@ -487,10 +544,10 @@ int mxc_parse_manifest(const char* basedir, const char* configfile, char** manif
     return MXD_OK;
 }
 
-int mxc_push_digest(mxd_ctx* ctx, const char* basedir, const char* configfile, int with_tree, char** manifest_json) {
+int mxc_push_digest(mxd_ctx* ctx, const char* basedir, const char* configfile, int flags, char** manifest_json) {
     if (!ctx || !basedir || !configfile || !manifest_json) return fail(MXD_ERR_INVALID, "push_digest: null argument");
     Manifest m;
-    int rc = push_digest(ctx, basedir, configfile, with_tree != 0, &m);
+    int rc = push_digest(ctx, basedir, configfile, flags, &m);
     if (rc != MXD_OK) return rc;
     *manifest_json = dup_out(json_manifest(m));
     return MXD_OK;
@@ -563,7 +620,7 @@ int mxc_push_local(mxd_ctx* ctx, const char* basedir, const char* configfile, co
     if (!ctx || !basedir || !configfile || !basepath || !repository || !version || !report_json)
         return fail(MXD_ERR_INVALID, "push_local: null argument");
     Manifest m;
-    int rc = push_digest(ctx, basedir, configfile, false, &m);
+    int rc = push_digest(ctx, basedir, configfile, 0, &m);
     if (rc != MXD_OK) return rc;
     std::vector<Descriptor*> all;
     for (auto& b : m.blobs) all.push_back(&b);

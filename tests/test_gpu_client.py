@@ -141,3 +141,25 @@ def test_put_blob_verify_rejects_wrong_digest(engine, tmp_path):
     assert reg.exists_blob("library/m", good)
     reg.put_blob("library/m", bad, str(src), verify=False)       # reference behaviour: stored unverified
     assert reg.exists_blob("library/m", bad)
+
+
+def test_push_digest_cache_skips_unchanged_files(engine, tmp_path):
+    """Opt-in digest cache: unchanged (size, mtime) -> no re-hash; a touched or edited file is re-hashed."""
+    d, files = _model(tmp_path, big=8_000_000)
+    cl = client.Client(engine)
+    first = cl.push_digest_json(str(d), use_cache=True)
+    cache = json.loads((d / ".modelx" / "digests.json").read_text())
+    assert set(cache) == set(files) and cache["README.md"]["digest"] == "sha256:" + hashlib.sha256(files["README.md"]).hexdigest()
+    b0 = engine.stats()["bytes_hashed"]
+    assert cl.push_digest_json(str(d), use_cache=True) == first
+    assert engine.stats()["bytes_hashed"] == b0                     # nothing was hashed the second time
+    assert cl.push_digest_json(str(d)) == first                     # and the uncached path agrees
+    # edit one file (same size, new mtime) and corrupt the cache entry of another: both get re-hashed correctly
+    time.sleep(0.01)
+    (d / "README.md").write_bytes(b"# MODEL\n")
+    m = json.loads(cl.push_digest_json(str(d), use_cache=True))
+    readme = [b for b in m["blobs"] if b["name"] == "README.md"][0]
+    assert readme["digest"] == "sha256:" + hashlib.sha256(b"# MODEL\n").hexdigest()
+    assert engine.stats()["bytes_hashed"] - b0 < 5_000_000 + 8_000_100          # only README (+ the uncached full pass above)
+    (d / ".modelx" / "digests.json").write_text("{broken")
+    assert json.loads(cl.push_digest_json(str(d), use_cache=True)) == m          # unreadable cache = no cache
