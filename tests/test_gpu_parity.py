@@ -386,3 +386,16 @@ def test_files_with_skewed_sizes(engine, tmp_path):
     with modelx_b200.Engine(devices=[0], ring_bytes=4 << 20) as small:       # 1 MiB slots: many rounds
         got2, _ = small.sha256_files(paths)
     assert got2 == want
+
+
+def test_tree_digest_of_unaligned_device_buffer(engine, oracle):
+    """Device-resident blob that starts at an odd address (e.g. a slice of a larger tensor)."""
+    torch = _torch()
+    rng = np.random.default_rng(9)
+    host = rng.integers(0, 256, size=5_000_011, dtype=np.uint8)
+    dev = torch.from_numpy(host).cuda()
+    for off in (1, 2, 3, 5, 8, 13):
+        n = host.size - off - (off % 7)
+        chunks, root = engine.tree_digest_ptr(dev.data_ptr() + off, n, 1 << 20, 16 << 10, 8)
+        want_chunks, _, want_root = oracle.tree_digest(host[off:off + n].tobytes(), 1 << 20, 16 << 10, 8)
+        assert (chunks, root) == (want_chunks, want_root), off
