@@ -14,7 +14,9 @@ namespace mxd {
 
 namespace {
 
-constexpr int kThreads = 128;
+// 64-thread CTAs: same throughput as 128 (profiles/r01_quick_bench_variants.txt) but half the work quantum per
+// CTA (1 MiB of leaves), which halves the drain at the end of a launch -- it matters at 12.5 GB per GPU (N=8).
+constexpr int kThreads = 64;
 
 __device__ __forceinline__ uint4 ldg128(const uint4* p) {
     uint4 v;
@@ -51,7 +53,7 @@ __device__ __forceinline__ void unpack_block(const uint4& v0, const uint4& v1, c
     w[12] = bswap32(v3.x); w[13] = bswap32(v3.y); w[14] = bswap32(v3.z); w[15] = bswap32(v3.w);
 }
 
-// MINB = resident CTAs per SM the register allocator must allow (6 -> 80 registers, 8 -> 63).
+// MINB = resident CTAs per SM the register allocator must allow (12 x 64 threads -> 80 registers, 16 -> 63).
 template <int MINB>
 __global__ void __launch_bounds__(kThreads, MINB) k_sha256_lanes(const MsgJob j) {
     const uint64_t m = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
@@ -369,9 +371,9 @@ __global__ void k_gen_fill(uint64_t* __restrict__ dst, uint64_t first_word, uint
 
 }  // namespace
 
-// Occupancy: 6 CTAs x 128 threads per SM (80 registers, 24 warps) is the default; 4..6 CTAs measure the same
-// (1.01 TB/s), 8 CTAs (63 registers) is 11 % slower (profiles/r01_quick_bench_v3.txt).  MXD_TUNE_MINB=8 keeps the
-// 8-CTA build selectable for A/B profiling.
+// Occupancy: 24 warps per SM at 80 registers is the default (16..24 warps measure the same, 1.01 TB/s); 32 warps
+// at 63 registers is 11 % slower (profiles/r01_quick_bench_v3.txt).  MXD_TUNE_MINB=8 keeps the 32-warp build
+// selectable for A/B profiling.
 static int g_minb = [] { const char* e = getenv("MXD_TUNE_MINB"); return (e && atoi(e) == 8) ? 8 : 6; }();
 
 static long g_coop_max = [] { const char* e = getenv("MXD_TUNE_COOP"); return e ? atol(e) : 8192L; }();
@@ -387,8 +389,8 @@ cudaError_t launch_sha256(const MsgJob& job, cudaStream_t stream) {
         k_sha256_chains_coop<<<(unsigned)cblocks, 64, 0, stream>>>(job);
         return cudaGetLastError();
     }
-    if (g_minb == 8) k_sha256_lanes<8><<<(unsigned)blocks, kThreads, 0, stream>>>(job);
-    else             k_sha256_lanes<6><<<(unsigned)blocks, kThreads, 0, stream>>>(job);
+    if (g_minb == 8) k_sha256_lanes<16><<<(unsigned)blocks, kThreads, 0, stream>>>(job);
+    else             k_sha256_lanes<12><<<(unsigned)blocks, kThreads, 0, stream>>>(job);
     return cudaGetLastError();
 }
 
@@ -416,7 +418,7 @@ cudaError_t launch_tree_root(uint64_t size, uint64_t leaf, uint32_t fanout, cons
 
 int sha256_kernel_regs() {
     cudaFuncAttributes a;
-    if (cudaFuncGetAttributes(&a, k_sha256_lanes<6>) != cudaSuccess) return -1;
+    if (cudaFuncGetAttributes(&a, k_sha256_lanes<12>) != cudaSuccess) return -1;
     return a.numRegs;
 }
 
