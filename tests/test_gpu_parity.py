@@ -399,3 +399,21 @@ def test_tree_digest_of_unaligned_device_buffer(engine, oracle):
         chunks, root = engine.tree_digest_ptr(dev.data_ptr() + off, n, 1 << 20, 16 << 10, 8)
         want_chunks, _, want_root = oracle.tree_digest(host[off:off + n].tobytes(), 1 << 20, 16 << 10, 8)
         assert (chunks, root) == (want_chunks, want_root), off
+
+
+def test_tree_golden_vectors_on_gpu(engine, oracle):
+    """The committed hashlib-made vectors (tests/golden/tree_golden.json) through the CUDA path."""
+    import json
+    with open(os.path.join(os.path.dirname(__file__), "golden", "tree_golden.json")) as f:
+        rows = json.load(f)
+    torch = _torch()
+    for r in rows:
+        # data generated ON the GPU by k_gen_fill at the golden offset, digested in place
+        n8 = (r["offset"] + r["size"] + 7) // 8 * 8
+        dev = torch.empty(max(n8, 8), dtype=torch.uint8, device="cuda")
+        engine.dev_gen_fill(0, dev.data_ptr(), 0, n8, r["seed"])
+        torch.cuda.synchronize()
+        ptr = dev.data_ptr() + r["offset"]
+        assert engine.sha256_ptr(ptr, r["size"]).hex() == r["sha256"]
+        chunks, root = engine.tree_digest_ptr(ptr, r["size"], r["chunk"], r["leaf"], r["fanout"])
+        assert [c.hex() for c in chunks] == r["chunks"] and root.hex() == r["root"], r["size"]

@@ -131,3 +131,16 @@ def test_generator_is_offset_consistent(oracle):
     for off, n in [(0, 1), (1, 7), (5, 100), (8, 64), (1000, 3096), (4095, 1)]:
         assert oracle.gen(off, n, seed=42) == whole[off:off + n]
     assert oracle.gen(0, 64, seed=43) != whole[:64]
+
+
+def test_tree_golden_vectors(oracle):
+    """tests/golden/tree_golden.json was produced with hashlib and a pure-Python splitmix64
+    (tests/golden/make_tree_golden.py): pins the generator, whole-message SHA-256 and the tree definition."""
+    with open(os.path.join(GOLDEN, "tree_golden.json")) as f:
+        rows = json.load(f)
+    assert len(rows) >= 9
+    for r in rows:
+        data = oracle.gen(r["offset"], r["size"], r["seed"])
+        assert oracle.sha256(data).hex() == r["sha256"]
+        chunks, _, root = oracle.tree_digest(data, r["chunk"], r["leaf"], r["fanout"])
+        assert [c.hex() for c in chunks] == r["chunks"] and root.hex() == r["root"], r["size"]
