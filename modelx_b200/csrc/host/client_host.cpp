@@ -52,21 +52,40 @@ struct Manifest {
 };
 
 // ---- encoding/json compatible output ------------------------------------------------------------------
+// encoding/json string encoding with HTML escaping on (the default of json.Marshal): ", \\, control
+// characters, <, >, &, U+2028/U+2029 are escaped; invalid UTF-8 becomes \ufffd.
 void json_string(std::string& o, const std::string& s) {
     static const char* hex = "0123456789abcdef";
     o += '"';
-    for (size_t i = 0; i < s.size(); ++i) {
-        unsigned char c = (unsigned char)s[i];
-        if (c == '"') o += "\\\"";
-        else if (c == '\\') o += "\\\\";
-        else if (c == '\n') o += "\\n";
-        else if (c == '\r') o += "\\r";
-        else if (c == '\t') o += "\\t";
-        else if (c < 0x20 || c == '<' || c == '>' || c == '&') { o += "\\u00"; o += hex[c >> 4]; o += hex[c & 15]; }
-        else if (c == 0xE2 && i + 2 < s.size() && (unsigned char)s[i + 1] == 0x80 &&
-                 ((unsigned char)s[i + 2] == 0xA8 || (unsigned char)s[i + 2] == 0xA9)) {
-            o += ((unsigned char)s[i + 2] == 0xA8) ? "\\u2028" : "\\u2029"; i += 2;
-        } else o += (char)c;
+    size_t i = 0;
+    while (i < s.size()) {
+        const unsigned char c = (unsigned char)s[i];
+        if (c < 0x80) {
+            if (c == '"') o += "\\\"";
+            else if (c == '\\') o += "\\\\";
+            else if (c == '\n') o += "\\n";
+            else if (c == '\r') o += "\\r";
+            else if (c == '\t') o += "\\t";
+            else if (c < 0x20 || c == '<' || c == '>' || c == '&') { o += "\\u00"; o += hex[c >> 4]; o += hex[c & 15]; }
+            else o += (char)c;
+            ++i; continue;
+        }
+        // decode one UTF-8 sequence (shortest form, no surrogates, <= U+10FFFF), as Go's utf8.DecodeRuneInString
+        int len = 0; uint32_t cp = 0;
+        if (c >= 0xC2 && c <= 0xDF) { len = 2; cp = c & 0x1F; }
+        else if (c >= 0xE0 && c <= 0xEF) { len = 3; cp = c & 0x0F; }
+        else if (c >= 0xF0 && c <= 0xF4) { len = 4; cp = c & 0x07; }
+        bool ok = len != 0 && i + (size_t)len <= s.size();
+        for (int k = 1; ok && k < len; ++k) {
+            const unsigned char cc = (unsigned char)s[i + k];
+            if ((cc & 0xC0) != 0x80) ok = false; else cp = (cp << 6) | (cc & 0x3F);
+        }
+        if (ok && ((len == 3 && (cp < 0x800 || (cp >= 0xD800 && cp <= 0xDFFF))) || (len == 4 && (cp < 0x10000 || cp > 0x10FFFF)))) ok = false;
+        if (!ok) { o += "\\ufffd"; ++i; continue; }
+        if (cp == 0x2028) o += "\\u2028";
+        else if (cp == 0x2029) o += "\\u2029";
+        else o.append(s, i, (size_t)len);
+        i += (size_t)len;
     }
     o += '"';
 }

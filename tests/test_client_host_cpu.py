@@ -119,3 +119,26 @@ def test_manifest_roundtrip_is_byte_stable(tmp_path):
     with pytest.raises(modelx_b200.MxdError) as ei:
         reg.get_manifest_json("library/m", "missing")
     assert ei.value.status == N.MXC_ERR_NOT_FOUND
+
+
+def test_json_string_escaping_follows_encoding_json(tmp_path):
+    """File names with quotes, control characters, non-ASCII, U+2028 and invalid UTF-8 are rendered as Go's
+    encoding/json would (HTML-safe escapes, invalid bytes -> \\ufffd)."""
+    d = tmp_path / "m"
+    d.mkdir()
+    (d / "modelx.yaml").write_text("x")
+    names = [b'q"uote', b"tab\there", b"uni-\xe6\xa8\xa1\xe5\x9e\x8b.bin", b"ls\xe2\x80\xa8sep", b"bad\xff\xfebytes", b"trunc\xe6\xa8", b"back\\slash"]
+    for n in names:
+        with open(os.path.join(os.fsencode(str(d)), n), "wb") as f:
+            f.write(b"1")
+    got = client.parse_manifest_json(str(d))
+    blobs = got[got.index('"blobs":['):]
+    for frag in ('"q\\"uote"', '"tab\\there"', '"uni-模型.bin"', '"ls\\u2028sep"', '"bad\\ufffd\\ufffdbytes"',
+                 '"trunc\\ufffd\\ufffd"', '"back\\\\slash"'):
+        assert frag in blobs, frag
+    m = json.loads(got)                       # and it is valid JSON
+    assert len(m["blobs"]) == len(names)
+    # byte-wise name order, as strings.Compare sorts them (push.go:98)
+    def go_decode(b):   # Go replaces every undecodable byte by one U+FFFD (Python's "replace" merges truncated sequences)
+        return "".join("\ufffd" if 0xDC80 <= ord(ch) <= 0xDCFF else ch for ch in b.decode("utf-8", "surrogateescape"))
+    assert [b["name"] for b in m["blobs"]] == [go_decode(n) for n in sorted(names)]
