@@ -129,6 +129,12 @@ int mxd_tree_finish(mxd_ctx*, const uint8_t* chunk_digests, uint64_t nchunks, ui
 int     mxd_calc_parts(int64_t total, int64_t partscount, mxd_part* out /*partscount*/);   /* calcParts, extension_s3.go:99-112 */
 int64_t mxd_server_part_count(int64_t size, int force_multipart);                         /* store_s3.go:198-203,273-279 */
 
+/* SHA-256 of each part [offset, offset+length) of one file, all parts advanced together as one GPU batch:
+ * the ranges S3Extension.Upload sends (extension_s3.go:52-89 over calcParts), e.g. for per-part
+ * x-amz-checksum-sha256.  New (the reference never hashes a part); each digest is the plain SHA-256 of that
+ * byte range.  Ranges may overlap or leave gaps; a range past EOF is MXD_ERR_IO. */
+int mxd_sha256_file_parts(mxd_ctx*, const char* path, const mxd_part* parts, uint64_t n, uint8_t* out /*n*32*/);
+
 /* ---- digest strings (go-digest v1.0.0; registry.go:218-227 BlobDigestFun accepts only this form) */
 void mxd_digest_string(const uint8_t d[32], char out[72]);      /* "sha256:" + 64 lower hex + NUL */
 int  mxd_digest_parse(const char* s, uint8_t out[32]);          /* MXD_ERR_INVALID unless exactly that form */

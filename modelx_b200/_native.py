@@ -61,6 +61,7 @@ PROTOTYPES = {
     "mxd_sha256_batch": (C.c_int, [vp, C.POINTER(Span), C.c_uint64, u8p]),
     "mxd_sha256_file": (C.c_int, [vp, C.c_char_p, u8p, u64p]),
     "mxd_sha256_files": (C.c_int, [vp, C.POINTER(C.c_char_p), C.c_uint64, u8p, u64p]),
+    "mxd_sha256_file_parts": (C.c_int, [vp, C.c_char_p, C.POINTER(Part), C.c_uint64, u8p]),
     "mxd_verify_batch": (C.c_int, [vp, C.POINTER(Span), u8p, C.c_uint64, u8p]),
     "mxd_verify_files": (C.c_int, [vp, C.POINTER(C.c_char_p), u8p, C.c_uint64, u8p]),
     "mxd_hasher_new": (C.c_int, [vp, C.POINTER(vp)]),

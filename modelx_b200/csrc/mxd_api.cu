@@ -1032,6 +1032,27 @@ int mxd_sha256_files(mxd_ctx* c, const char* const* paths, uint64_t n, uint8_t* 
     return rc;
 }
 
+int mxd_sha256_file_parts(mxd_ctx* c, const char* path, const mxd_part* parts, uint64_t n, uint8_t* out) {
+    if (!c || !path || (n && (!parts || !out))) return fail(MXD_ERR_INVALID, "sha256_file_parts: bad arguments");
+    if (n == 0) return MXD_OK;
+    int fd = open(path, O_RDONLY | O_CLOEXEC);
+    if (fd < 0) return fail(MXD_ERR_IO, std::string("open ") + path + ": " + strerror(errno));
+    struct stat st;
+    if (fstat(fd, &st) != 0) { int e = errno; close(fd); errno = e; return fail(MXD_ERR_IO, std::string("fstat: ") + strerror(e)); }
+    LockstepInput in;
+    in.src.resize(n); in.len.resize(n);
+    for (uint64_t i = 0; i < n; ++i) {
+        if (parts[i].offset < 0 || parts[i].length < 0 || (uint64_t)parts[i].offset + (uint64_t)parts[i].length > (uint64_t)st.st_size) {
+            close(fd);
+            return fail(MXD_ERR_IO, "sha256_file_parts: part " + std::to_string(i) + " lies outside the file");
+        }
+        in.src[i].fd = fd; in.src[i].base = (uint64_t)parts[i].offset; in.len[i] = (uint64_t)parts[i].length;
+    }
+    int rc = lockstep_digest_all(c, in, out);
+    close(fd);
+    return rc;
+}
+
 int mxd_sha256_file(mxd_ctx* c, const char* path, uint8_t out[32], uint64_t* size) {
     if (!path) return fail(MXD_ERR_INVALID, "sha256_file: null path");
     const char* paths[1] = {path};

@@ -184,6 +184,17 @@ class Engine:
         raw = bytes(out)
         return [raw[32 * i:32 * i + 32] for i in range(n)], [int(sizes[i]) for i in range(n)]
 
+    def sha256_file_parts(self, path: str, parts: Sequence[Tuple[int, int]]) -> List[bytes]:
+        """SHA-256 of each (offset, length) range of a file, e.g. the ranges calc_parts() yields."""
+        n = len(parts)
+        arr = (N.Part * max(n, 1))()
+        for i, (off, ln) in enumerate(parts):
+            arr[i].offset, arr[i].length = off, ln
+        out = (C.c_uint8 * (32 * max(n, 1)))()
+        N.check(self._lib.mxd_sha256_file_parts(self._ctx, path.encode(), arr, n, out), "mxd_sha256_file_parts")
+        raw = bytes(out)
+        return [raw[32 * i:32 * i + 32] for i in range(n)]
+
     def verify_batch(self, items: Iterable, want: Sequence[bytes]) -> List[bool]:
         bufs = [_buf(x) for x in items]
         n = len(bufs)

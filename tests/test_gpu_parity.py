@@ -417,3 +417,22 @@ def test_tree_golden_vectors_on_gpu(engine, oracle):
         assert engine.sha256_ptr(ptr, r["size"]).hex() == r["sha256"]
         chunks, root = engine.tree_digest_ptr(ptr, r["size"], r["chunk"], r["leaf"], r["fanout"])
         assert [c.hex() for c in chunks] == r["chunks"] and root.hex() == r["root"], r["size"]
+
+
+def test_file_part_digests_follow_calc_parts(engine, tmp_path):
+    """calcParts (extension_s3.go:99-112) feeding per-part digests: the multipart split and the hash as one call."""
+    rng = random.Random(5)
+    data = rng.randbytes(50_000_017)
+    p = tmp_path / "blob.bin"
+    p.write_bytes(data)
+    for nparts in (1, 3, 7):
+        parts = modelx_b200.calc_parts(len(data), nparts)
+        got = engine.sha256_file_parts(str(p), parts)
+        assert got == [hashlib.sha256(data[o:o + l]).digest() for o, l in parts]
+    # 8 MiB "multipart chunks" as in BASELINE config 4, plus overlapping / empty ranges
+    parts = [(o, min(8 << 20, len(data) - o)) for o in range(0, len(data), 8 << 20)] + [(5, 0), (1, 100), (0, len(data))]
+    got = engine.sha256_file_parts(str(p), parts)
+    assert got == [hashlib.sha256(data[o:o + l]).digest() for o, l in parts]
+    with pytest.raises(modelx_b200.MxdError) as ei:
+        engine.sha256_file_parts(str(p), [(len(data) - 10, 11)])
+    assert ei.value.status == -4
