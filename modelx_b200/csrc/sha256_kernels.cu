@@ -161,13 +161,17 @@ __global__ void __launch_bounds__(kThreads, MINB) k_sha256_lanes(const MsgJob j)
 // kernel above is latency bound: a lone warp needs ~3,300 clk per block because the 480-instruction
 // message schedule and the loads sit in the same instruction stream as the 64 dependent rounds.
 // Here every 32 chains get two warps on two different SM sub-partitions:
-//   warp 1 (producer)  loads/pads block b of its 32 messages, expands the schedule and stores
-//                      W[t]+K[t] (t = 0..63) to shared memory, one stage ahead;
-//   warp 0 (chain)     runs only the 64 rounds, reading W[t]+K[t] with LDS.128 (16 per block).
-// The chain warp's critical path is then ~18 clk per round.  Same MsgJob contract as the lanes kernel
+//   warp 1 (producer)  loads/pads block b of its 32 messages (next block prefetched into registers), expands
+//                      the schedule and stores W[t]+K[t] (t = 0..63) to shared memory, one stage ahead;
+//   warp 0 (chain)     runs only the 64 rounds, reading W[t]+K[t] with LDS.128 (16 per block), with the
+//                      round written so that a single addition follows Sigma1 on the e-chain.
+// Measured 69-73 MB/s per chain against 38 MB/s in the lanes kernel (profiles/r01_batch_bench_coop_v2.txt).  Same MsgJob contract as the lanes kernel
 // (spans or segments, chained state, per-message control bytes), same results bit for bit.
 // =====================================================================================================
 constexpr int kCoopStages = 2;
+#ifndef MXD_COOP_SHORT_CHAIN
+#define MXD_COOP_SHORT_CHAIN 1
+#endif
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(nthreads) : "memory"); }
@@ -211,21 +215,65 @@ __global__ void __launch_bounds__(64) k_sha256_chains_coop(const MsgJob j) {
 
     if (role == 1) {
         // ---------------- producer: load / pad, expand, publish W+K ---------------------------------
-        constexpr K256Table K = k256_table();
+        // expands w[16] to the 64 schedule words, adds the round constants and publishes them for `lane`
+        auto expand_store = [&](uint32_t (&w)[16], int st) {
+            constexpr K256Table K = k256_table();
+#pragma unroll
+            for (int g = 0; g < 16; ++g) {
+                uint32_t o4[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int t = 4 * g + q;
+                    if (t >= 16) {
+                        uint32_t x = add_fma(w[t & 15], small_sigma0(w[(t + 1) & 15]), one);
+                        x = add_fma(x, w[(t + 9) & 15], one);
+                        w[t & 15] = add_fma(x, small_sigma1(w[(t + 14) & 15]), one);
+                    }
+                    o4[q] = add_fma(w[t & 15], K.v[t], one);
+                }
+                wk[st][g][lane] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+            }
+        };
         const bool warp_aligned = __all_sync(0xffffffffu, (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0);
         uint32_t w[16];
-        for (uint64_t b = 0; b < nmax; ++b) {
+        uint64_t b = 0;
+        if (warp_aligned) {
+            // Hot loop (aligned messages): the next block is prefetched into registers while this one is expanded,
+            // so the chain warp never waits for DRAM.  Runs while ANY lane still has full blocks; lanes that ran
+            // out keep re-reading their last block (or nothing) and publish nothing.
+            // Lanes without a message (tail of the batch, finished files) shadow a live lane so that they do not
+            // force the whole warp onto the slow path: same address, same trip count, nothing of theirs is consumed.
+            const unsigned have = __ballot_sync(0xffffffffu, nblk > 0 && nfull > 0);
+            const int src = have ? (__ffs(have) - 1) : 0;
+            const uint64_t src_ptr = __shfl_sync(0xffffffffu, reinterpret_cast<uint64_t>(ptr), src);
+            const uint64_t src_nfull = __shfl_sync(0xffffffffu, nfull, src);
+            const bool shadow = (nblk == 0);      // only lanes the chain warp will never read for
+            const uint8_t* hot_ptr = shadow ? reinterpret_cast<const uint8_t*>(src_ptr) : ptr;
+            const uint64_t hot_nfull = shadow ? src_nfull : nfull;
+            uint64_t nfull_min = have ? hot_nfull : 0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { const uint64_t other = __shfl_xor_sync(0xffffffffu, nfull_min, o); nfull_min = other < nfull_min ? other : nfull_min; }
+            if (nfull_min > 0) {
+                const uint4* p4 = reinterpret_cast<const uint4*>(hot_ptr);
+                uint4 v0 = ldg128(p4), v1 = ldg128(p4 + 1), v2 = ldg128(p4 + 2), v3 = ldg128(p4 + 3);
+                for (; b < nfull_min; ++b) {          // every lane has a full block b here: no divergence, no merges
+                    const int st = (int)(b % kCoopStages);
+                    if (b >= (uint64_t)kCoopStages) named_bar_sync(kEmpty0 + st, 64);
+                    unpack_block(v0, v1, v2, v3, w);
+                    p4 += (b + 1 < hot_nfull) ? 4 : 0;
+                    v0 = ldg128(p4); v1 = ldg128(p4 + 1); v2 = ldg128(p4 + 2); v3 = ldg128(p4 + 3);
+                    expand_store(w, st);
+                    named_bar_arrive(kFull0 + st, 64);
+                }
+            }
+        }
+        // Everything else: ragged tails of the batch, unaligned messages, padding and length blocks.
+        for (; b < nmax; ++b) {
             const int st = (int)(b % kCoopStages);
             if (b >= (uint64_t)kCoopStages) named_bar_sync(kEmpty0 + st, 64);   // chain warp has drained this stage
             if (b < nblk) {
                 if (b < nfull) {
-                    if (warp_aligned) {
-                        const uint4* p4 = reinterpret_cast<const uint4*>(ptr + (b << 6));
-                        const uint4 v0 = ldg128(p4), v1 = ldg128(p4 + 1), v2 = ldg128(p4 + 2), v3 = ldg128(p4 + 3);
-                        unpack_block(v0, v1, v2, v3, w);
-                    } else {
-                        load_block_unaligned(ptr + (b << 6), w);
-                    }
+                    load_block_unaligned(ptr + (b << 6), w);
                 } else if (b == nfull) {
                     const uint8_t* t = ptr + (nfull << 6);
 #pragma unroll
@@ -245,21 +293,7 @@ __global__ void __launch_bounds__(64) k_sha256_chains_coop(const MsgJob j) {
                     for (int k = 0; k < 14; ++k) w[k] = 0;
                     w[14] = (uint32_t)(bits >> 32); w[15] = (uint32_t)bits;
                 }
-#pragma unroll
-                for (int g = 0; g < 16; ++g) {
-                    uint32_t o4[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int t = 4 * g + q;
-                        if (t >= 16) {
-                            uint32_t x = add_fma(w[t & 15], small_sigma0(w[(t + 1) & 15]), one);
-                            x = add_fma(x, w[(t + 9) & 15], one);
-                            w[t & 15] = add_fma(x, small_sigma1(w[(t + 14) & 15]), one);
-                        }
-                        o4[q] = add_fma(w[t & 15], K.v[t], one);
-                    }
-                    wk[st][g][lane] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
-                }
+                expand_store(w, st);
             }
             named_bar_arrive(kFull0 + st, 64);
         }
@@ -291,12 +325,24 @@ __global__ void __launch_bounds__(64) k_sha256_chains_coop(const MsgJob j) {
                     uint32_t& a = s[(0 - t) & 7]; uint32_t& bb = s[(1 - t) & 7]; uint32_t& c = s[(2 - t) & 7];
                     uint32_t& d = s[(3 - t) & 7]; uint32_t& e = s[(4 - t) & 7]; uint32_t& f = s[(5 - t) & 7];
                     uint32_t& gg = s[(6 - t) & 7]; uint32_t& hh = s[(7 - t) & 7];
+#if MXD_COOP_SHORT_CHAIN
+                    // latency-bound warp: keep only one addition behind Sigma1 on the e-chain (one extra IMAD per round)
+                    uint32_t y = add_fma(wkq[q], hh, one);
+                    y = add_fma(y, ch(e, f, gg), one);
+                    const uint32_t s1 = big_sigma1(e);
+                    const uint32_t x = add_fma(d, y, one);
+                    const uint32_t z = add_fma(y, maj(a, bb, c), one);
+                    d = add_fma(x, s1, one);
+                    const uint32_t z2 = add_fma(z, s1, one);
+                    hh = add_fma(z2, big_sigma0(a), one);
+#else
                     uint32_t t1 = add_fma(wkq[q], hh, one);
                     t1 = add_fma(t1, ch(e, f, gg), one);
                     t1 = add_fma(t1, big_sigma1(e), one);
                     d = add_fma(d, t1, one);
                     const uint32_t t2 = add_fma(big_sigma0(a), maj(a, bb, c), one);
                     hh = add_fma(t1, t2, one);
+#endif
                 }
             }
 #pragma unroll
@@ -376,14 +422,14 @@ __global__ void k_gen_fill(uint64_t* __restrict__ dst, uint64_t first_word, uint
 // selectable for A/B profiling.
 static int g_minb = [] { const char* e = getenv("MXD_TUNE_MINB"); return (e && atoi(e) == 8) ? 8 : 6; }();
 
-static long g_coop_max = [] { const char* e = getenv("MXD_TUNE_COOP"); return e ? atol(e) : 8192L; }();
+static long g_coop_max = [] { const char* e = getenv("MXD_TUNE_COOP"); return e ? atol(e) : 32768L; }();
 
 cudaError_t launch_sha256(const MsgJob& job, cudaStream_t stream) {
     if (job.nmsg == 0) return cudaSuccess;
     const uint64_t blocks = (job.nmsg + kThreads - 1) / kThreads;
     if (blocks > 0x7fffffffull) return cudaErrorInvalidValue;
-    // Few, long chains: two warps per 32 chains (see k_sha256_chains_coop).  Above ~8k chains the lanes kernel
-    // already keeps the ALU pipe busy and is the better choice.  MXD_TUNE_COOP=0 disables, =N sets the threshold.
+    // Few, long chains: two warps per 32 chains (see k_sha256_chains_coop).  Measured crossover with the lanes kernel
+    // is between 16k chains (coop 675 vs 610 GB/s) and 64k (791 vs 834).  MXD_TUNE_COOP=0 disables, =N sets the threshold.
     if (job.nmsg <= (uint64_t)g_coop_max) {
         const uint64_t cblocks = (job.nmsg + 31) / 32;
         k_sha256_chains_coop<<<(unsigned)cblocks, 64, 0, stream>>>(job);
