@@ -691,13 +691,13 @@ int mxd_open(mxd_ctx** out, const int* devices, int ndev, uint64_t ring_bytes) {
     auto* c = new mxd_ctx();
     int prev = -1; cudaGetDevice(&prev);
     int rc = MXD_OK;
-    // slot-filler threads per device: MXD_STAGE_THREADS, default min(32, hw threads / devices), at least 1
-    // (page-cache pread runs at 2-4 GB/s per thread; 16 threads gave 43 GB/s, the link moves 55)
+    // slot-filler threads per device: MXD_STAGE_THREADS, default min(16, hw threads / devices), at least 1
+    // (page-cache pread runs at 2-4 GB/s per thread; 16 threads gave 43.5 GB/s from a tmpfs file, 32 only 30.5)
     int stage_threads = 0;
     if (const char* env = getenv("MXD_STAGE_THREADS")) stage_threads = atoi(env);
     if (stage_threads <= 0) {
         const unsigned hw = std::thread::hardware_concurrency();
-        stage_threads = (int)std::min<unsigned>(32, std::max<unsigned>(1, hw / (unsigned)ords.size()));
+        stage_threads = (int)std::min<unsigned>(16, std::max<unsigned>(1, hw / (unsigned)ords.size()));
     }
     for (int ord : ords) {
         auto* d = new DevState();
