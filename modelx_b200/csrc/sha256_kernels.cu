@@ -4,8 +4,10 @@
 //   - batches of whole blobs (arbitrary spans; the reference's one-digest-per-file semantics,
 //     pkg/client/push.go:149-161 and pull.go:115-123, across many files at once),
 //   - chained segments of a single stream (hash.Hash-shaped incremental API, helper.go:46).
-// Pure 32-bit integer work: no tensor cores, no shared memory (the 16-word schedule and the
-// chain state live in registers; round constants are instruction immediates).
+// Pure 32-bit integer work, no tensor cores.  In the throughput kernel (k_sha256_lanes) the 16-word schedule
+// and the chain state live in registers and round constants are instruction immediates (no shared memory);
+// the latency kernel for few long chains (k_sha256_chains_coop) passes W+K between two warps through 16 KB
+// of shared memory.
 #include "kernels.h"
 #include "sha256_device.cuh"
 #include <cstdlib>
@@ -14,8 +16,8 @@ namespace mxd {
 
 namespace {
 
-// 64-thread CTAs: same throughput as 128 (profiles/r01_quick_bench_variants.txt) but half the work quantum per
-// CTA (1 MiB of leaves), which halves the drain at the end of a launch -- it matters at 12.5 GB per GPU (N=8).
+// 64-thread CTAs: measured identical to 128 threads at 12.5, 20 and 100 GB (profiles/r01_quick_bench_variants.txt);
+// kept for the finer work quantum per CTA (1 MiB of leaves).
 constexpr int kThreads = 64;
 
 __device__ __forceinline__ uint4 ldg128(const uint4* p) {
