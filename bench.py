@@ -261,11 +261,19 @@ def run_b200(args):
     leaf_bytes = prof["bytes"] / max(prof["launches"], 1)
     achieved = leaf_bytes / (leaf_ms * 1e-3) / GB if leaf_ms > 0 else 0.0
     tr = load_traffic()
+    # the bound that actually binds: ALU-pipe issue (2 warp-instr/clk/SM measured; 1,056 ALU-pipe instructions per
+    # 64-byte block of 32 lanes: 672 SHF + 352 LOP3 + 16 PRMT + 16 loop/address) at the SM clock seen under load
+    props = torch.cuda.get_device_properties(dev)
+    sm_clk_hz = (clocks["sm_mhz"] if (clocks and clocks.get("sm_mhz")) else 1965.0) * 1e6
+    alu_ceiling = 4 * 32 * 64 / (1056 * 2.0) * props.multi_processor_count * sm_clk_hz / GB
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": (tr["dram_bytes_per_algorithmic_byte"] * leaf_bytes) if tr else None,
                 "kernel": "k_sha256_lanes (leaf level)", "kernel_ms_per_launch": leaf_ms,
                 "algorithmic_bytes_per_launch": leaf_bytes, "kernel_share_of_step": prof["kernel_ms"] / ms if ms else None,
                 "peak_source": peak_src,
+                "alu_pipe": {"ceiling": alu_ceiling, "unit": "GB/s", "frac": achieved / alu_ceiling if alu_ceiling else None,
+                             "how": "4 SMSP x 32 lanes x 64 B / (1056 ALU-pipe instr x 2 clk) x SMs x SM clock; pipe rates "
+                                    "measured in profiles/r01_pipes_ubench.txt"},
                 "note": ("SHA-256 is 1 B read per B digested but ~16.5 INT32 ALU-pipe instructions per byte; the binding "
                          "limit is the ALU pipe (2 warp-instr/clk/SM measured), ceiling ~1.13 TB/s = 17% of HBM peak; "
                          "see DESIGN.md section 5")}
