@@ -17,6 +17,7 @@ import "C"
 import (
 	"context"
 	"fmt"
+	"os"
 	"sync"
 	"unsafe"
 
@@ -113,14 +114,19 @@ func TreeDigest(path string) (root digest.Digest, chunks []digest.Digest, size i
 	}
 	cpath := C.CString(path)
 	defer C.free(unsafe.Pointer(cpath))
+	fi, err := os.Stat(path)
+	if err != nil {
+		return "", nil, 0, err
+	}
+	const chunk = 8 << 20 // default mxd_tree_params: chunk 8 MiB, leaf 16 KiB, fanout 8
+	capChunks := (fi.Size() + chunk - 1) / chunk
+	if capChunks == 0 {
+		capChunks = 1
+	}
 	var n, sz C.uint64_t
 	var r [32]C.uint8_t
-	// first call sizes the chunk list (chunk_digests == NULL), second fills it
-	if rc := C.mxd_tree_digest_file(c, cpath, nil, nil, 0, &n, &sz, &r[0]); rc != C.MXD_OK {
-		return "", nil, 0, mxdError(rc)
-	}
-	buf := make([]C.uint8_t, 32*int(n))
-	if rc := C.mxd_tree_digest_file(c, cpath, nil, &buf[0], n, &n, &sz, &r[0]); rc != C.MXD_OK {
+	buf := make([]C.uint8_t, 32*int(capChunks))
+	if rc := C.mxd_tree_digest_file(c, cpath, nil, &buf[0], C.uint64_t(capChunks), &n, &sz, &r[0]); rc != C.MXD_OK {
 		return "", nil, 0, mxdError(rc)
 	}
 	var s [72]C.char
