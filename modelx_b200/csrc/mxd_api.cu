@@ -40,6 +40,18 @@ int fail(int status, const std::string& msg) {
             return fail(MXD_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));          \
     } while (0)
 
+// MXD_DEBUG_TIMING=1: print host-side phase timings of the streaming calls to stderr (developer aid)
+static const bool g_dbg_timing = getenv("MXD_DEBUG_TIMING") != nullptr;
+struct PhaseTimer {
+    const char* what; timespec t0;
+    explicit PhaseTimer(const char* w) : what(w) { if (g_dbg_timing) clock_gettime(CLOCK_MONOTONIC, &t0); }
+    ~PhaseTimer() {
+        if (!g_dbg_timing) return;
+        timespec t1; clock_gettime(CLOCK_MONOTONIC, &t1);
+        fprintf(stderr, "[mxd] %-28s %9.3f ms\n", what, (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6);
+    }
+};
+
 constexpr uint64_t kDefaultRingBytes = 256ull << 20;
 const uint32_t kIVHost[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au, 0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
 constexpr int kSlots = 4;
@@ -152,6 +164,8 @@ struct DevState {
     cudaEvent_t ev_copied[kSlots] = {}, ev_done[kSlots] = {};
     std::mutex mu;               // one streaming operation per device at a time
     StagePool* pool = nullptr;   // slot fillers for this device
+    uint8_t* h_desc = nullptr;   // pinned per-round descriptors of lock-step batches (grown on demand, under mu)
+    uint64_t h_desc_bytes = 0;
 };
 
 }  // namespace
@@ -365,7 +379,8 @@ int stream_segments(mxd_ctx* c, DevState* d, const Source& src, uint64_t nbytes,
         uint8_t* h_slot = d->h_ring + (uint64_t)s * d->slot_bytes;
         uint8_t* d_slot = d->d_ring + (uint64_t)s * d->slot_bytes;
         const uint8_t* from = nullptr;
-        int rc = source_stage(src, off, n, h_slot, &from, d->pool);
+        int rc;
+        { PhaseTimer pt("  fill slot"); rc = source_stage(src, off, n, h_slot, &from, d->pool); }
         if (rc != MXD_OK) return rc;
         MXD_CUDA(cudaMemcpyAsync(d_slot, from, n, cudaMemcpyHostToDevice, d->copy));
         MXD_CUDA(cudaEventRecord(d->ev_copied[s], d->copy));
@@ -383,13 +398,15 @@ int stream_segments(mxd_ctx* c, DevState* d, const Source& src, uint64_t nbytes,
 int stream_tree_chunks(mxd_ctx* c, DevState* d, const Tree& t, const Source& src, uint64_t nbytes, uint8_t* d_chunks) {
     const uint64_t n0 = nbytes ? (nbytes + t.leaf - 1) / t.leaf : 1;
     uint8_t* d_leaves = nullptr;
-    MXD_CUDA(cudaMalloc(&d_leaves, n0 * 32));
-    int rc = stream_segments(c, d, src, nbytes, t.leaf, d_leaves);
+    { PhaseTimer pt("alloc leaf digests"); MXD_CUDA(cudaMallocAsync(&d_leaves, n0 * 32, d->compute)); }
+    int rc;
+    { PhaseTimer pt("stream_segments (enqueue)"); rc = stream_segments(c, d, src, nbytes, t.leaf, d_leaves); }
     if (rc == MXD_OK) rc = enqueue_leaves_to_chunks(c, t, d_leaves, n0, d_chunks, d->compute);
     if (rc != MXD_OK) cudaStreamSynchronize(d->copy);   // nothing may still be reading the caller's (pinned) memory
-    cudaError_t e = cudaStreamSynchronize(d->compute);
+    cudaError_t e;
+    { PhaseTimer pt("sync compute"); e = cudaStreamSynchronize(d->compute); }
     if (rc == MXD_OK && e != cudaSuccess) rc = fail(MXD_ERR_CUDA, std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e));
-    cudaFree(d_leaves);
+    cudaFreeAsync(d_leaves, d->compute);
     return rc;
 }
 
@@ -411,15 +428,17 @@ int host_tree_chunks_all(mxd_ctx* c, const Tree& t, const Source& src, uint64_t 
         Source piece = src;
         if (piece.fd >= 0) piece.base += b0; else piece.mem += b0;
         uint8_t* d_chunks = nullptr;
-        cudaError_t e = cudaMalloc(&d_chunks, (c1 - c0) * 32);
+        cudaError_t e = cudaMallocAsync(&d_chunks, (c1 - c0) * 32, d->compute);
         if (e != cudaSuccess) { rcs[g] = MXD_ERR_CUDA; errs[g] = cudaGetErrorString(e); return; }
         int rc = stream_tree_chunks(c, d, t, piece, b1 - b0, d_chunks);
         if (rc == MXD_OK) {
-            e = cudaMemcpy(out + c0 * 32, d_chunks, (c1 - c0) * 32, cudaMemcpyDeviceToHost);
+            PhaseTimer pt("chunk digests D2H");
+            e = cudaMemcpyAsync(out + c0 * 32, d_chunks, (c1 - c0) * 32, cudaMemcpyDeviceToHost, d->compute);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(d->compute);
             if (e != cudaSuccess) { rc = MXD_ERR_CUDA; g_last_error = cudaGetErrorString(e); }
             c->d2h += (c1 - c0) * 32;
         }
-        cudaFree(d_chunks);
+        cudaFreeAsync(d_chunks, d->compute);
         rcs[g] = rc;
         if (rc != MXD_OK) errs[g] = g_last_error;
     };
@@ -438,10 +457,11 @@ int host_tree_chunks_all(mxd_ctx* c, const Tree& t, const Source& src, uint64_t 
 // upper levels + root from a host-resident chunk list (tiny: 32 B per chunk)
 int host_tree_finish(mxd_ctx* c, DevState* d, const Tree& t, const uint8_t* chunks, uint64_t nchunks, uint64_t size,
                      uint8_t root[32]) {
+    PhaseTimer pt("tree finish (levels + root)");
     std::lock_guard<std::mutex> lk(d->mu);
     DeviceGuard guard(d->ordinal);
     uint8_t* d_buf = nullptr;
-    MXD_CUDA(cudaMalloc(&d_buf, nchunks * 32 + 32));
+    MXD_CUDA(cudaMallocAsync(&d_buf, nchunks * 32 + 32, d->compute));
     int rc = MXD_OK;
     cudaError_t e = cudaMemcpyAsync(d_buf, chunks, nchunks * 32, cudaMemcpyHostToDevice, d->compute);
     if (e != cudaSuccess) rc = fail(MXD_ERR_CUDA, cudaGetErrorString(e));
@@ -454,7 +474,7 @@ int host_tree_finish(mxd_ctx* c, DevState* d, const Tree& t, const uint8_t* chun
     } else {
         cudaStreamSynchronize(d->compute);
     }
-    cudaFree(d_buf);
+    cudaFreeAsync(d_buf, d->compute);
     return rc;
 }
 
@@ -485,19 +505,29 @@ int lockstep_digest(mxd_ctx* c, DevState* d, const LockstepInput& in, uint8_t* o
 
     // per-round descriptors live in pinned memory, double-buffered per slot
     const uint64_t desc_bytes = (n * (sizeof(mxd::DevSpan) + sizeof(uint64_t) + 1) + 255) & ~255ull;
-    uint8_t *h_desc = nullptr, *d_desc = nullptr, *d_out = nullptr;
+    // Scratch: pinned descriptors are kept in the device state (cudaMallocHost costs ~0.5 ms, too much for small
+    // calls); device buffers come from the stream-ordered pool, which mxd_open told to keep freed memory cached.
+    if (d->h_desc_bytes < desc_bytes * kSlots) {
+        if (d->h_desc) cudaFreeHost(d->h_desc);
+        d->h_desc = nullptr; d->h_desc_bytes = 0;
+        const uint64_t want = std::max<uint64_t>(desc_bytes * kSlots, 64 << 10);
+        MXD_CUDA(cudaHostAlloc(&d->h_desc, want, cudaHostAllocPortable));
+        d->h_desc_bytes = want;
+    }
+    uint8_t *h_desc = d->h_desc, *d_desc = nullptr, *d_out = nullptr;
     uint32_t* d_state = nullptr;
-    MXD_CUDA(cudaMallocHost(&h_desc, desc_bytes * kSlots));
     int rc = MXD_OK;
     cudaError_t e;
-    if ((e = cudaMalloc(&d_desc, desc_bytes * kSlots)) != cudaSuccess ||
-        (e = cudaMalloc(&d_out, n * 32)) != cudaSuccess || (e = cudaMalloc(&d_state, n * 32)) != cudaSuccess) {
-        rc = fail(MXD_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    if ((e = cudaMallocAsync(&d_desc, desc_bytes * kSlots, d->compute)) != cudaSuccess ||
+        (e = cudaMallocAsync(&d_out, n * 32, d->compute)) != cudaSuccess ||
+        (e = cudaMallocAsync(&d_state, n * 32, d->compute)) != cudaSuccess) {
+        rc = fail(MXD_ERR_CUDA, std::string("cudaMallocAsync: ") + cudaGetErrorString(e));
     }
     if (rc == MXD_OK) {  // every chain starts from the FIPS 180-4 initial hash value
         std::vector<uint32_t> iv(n * 8);
         for (uint64_t i = 0; i < n; ++i) memcpy(&iv[8 * i], kIVHost, 32);
-        e = cudaMemcpy(d_state, iv.data(), n * 32, cudaMemcpyHostToDevice);
+        e = cudaMemcpyAsync(d_state, iv.data(), n * 32, cudaMemcpyHostToDevice, d->compute);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(d->compute);   // iv is a stack/heap temporary; also orders the pool allocations before the copy stream uses them
         if (e != cudaSuccess) rc = fail(MXD_ERR_CUDA, cudaGetErrorString(e));
     }
     for (uint64_t k = 0; running > 0 && rc == MXD_OK; ++k) {
@@ -561,14 +591,16 @@ int lockstep_digest(mxd_ctx* c, DevState* d, const LockstepInput& in, uint8_t* o
         c->launches++; c->bytes_hashed += moved; c->h2d += span_bytes + desc_bytes;
     }
     if (rc == MXD_OK) {
-        e = cudaStreamSynchronize(d->compute);
-        if (e == cudaSuccess) e = cudaMemcpy(out, d_out, n * 32, cudaMemcpyDeviceToHost);
+        e = cudaMemcpyAsync(out, d_out, n * 32, cudaMemcpyDeviceToHost, d->compute);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(d->compute);
         if (e != cudaSuccess) rc = fail(MXD_ERR_CUDA, cudaGetErrorString(e));
         c->d2h += n * 32;
     } else {
         cudaStreamSynchronize(d->compute); cudaStreamSynchronize(d->copy);
     }
-    cudaFree(d_state); cudaFree(d_out); cudaFree(d_desc); cudaFreeHost(h_desc);
+    if (d_state) cudaFreeAsync(d_state, d->compute);
+    if (d_out) cudaFreeAsync(d_out, d->compute);
+    if (d_desc) cudaFreeAsync(d_desc, d->compute);
     return rc;
 }
 
@@ -745,6 +777,7 @@ void mxd_close(mxd_ctx* c) {
         }
         if (d->h_ring) cudaFreeHost(d->h_ring);
         if (d->d_ring) cudaFree(d->d_ring);
+        if (d->h_desc) cudaFreeHost(d->h_desc);
         delete d->pool;
         delete d;
     }
@@ -908,7 +941,7 @@ int mxd_tree_chunks(mxd_ctx* c, const void* piece, uint64_t nbytes, const mxd_tr
         std::lock_guard<std::mutex> lk(d->mu);
         DeviceGuard guard(d->ordinal);
         uint8_t* d_chunks = nullptr;
-        MXD_CUDA(cudaMalloc(&d_chunks, nchunks * 32));
+        MXD_CUDA(cudaMallocAsync(&d_chunks, nchunks * 32, d->compute));   // cudaMalloc/cudaFree cost ~6 ms a pair on this box
         int rc = enqueue_tree_chunks(c, t, static_cast<const uint8_t*>(piece), nbytes, d_chunks, d->compute);
         if (rc == MXD_OK) {
             cudaError_t e = cudaMemcpyAsync(out, d_chunks, nchunks * 32, cudaMemcpyDeviceToHost, d->compute);
@@ -916,7 +949,7 @@ int mxd_tree_chunks(mxd_ctx* c, const void* piece, uint64_t nbytes, const mxd_tr
             if (e != cudaSuccess) rc = fail(MXD_ERR_CUDA, cudaGetErrorString(e));
             c->d2h += nchunks * 32;
         }
-        cudaFree(d_chunks);
+        cudaFreeAsync(d_chunks, d->compute);
         return rc;
     }
     Source src; src.mem = static_cast<const uint8_t*>(piece); src.pinned = (kind == MemKind::Pinned);
@@ -992,7 +1025,7 @@ int mxd_sha256_batch(mxd_ctx* c, const mxd_span* spans, uint64_t n, uint8_t* out
         std::lock_guard<std::mutex> lk(d->mu);
         DeviceGuard guard(d->ordinal);
         uint8_t* d_buf = nullptr;
-        MXD_CUDA(cudaMalloc(&d_buf, n * (sizeof(mxd_span) + 32)));
+        MXD_CUDA(cudaMallocAsync(&d_buf, n * (sizeof(mxd_span) + 32), d->compute));
         int rc = MXD_OK;
         uint64_t total = 0; for (uint64_t i = 0; i < n; ++i) total += spans[i].len;
         cudaError_t e = cudaMemcpyAsync(d_buf, spans, n * sizeof(mxd_span), cudaMemcpyHostToDevice, d->compute);
@@ -1006,7 +1039,7 @@ int mxd_sha256_batch(mxd_ctx* c, const mxd_span* spans, uint64_t n, uint8_t* out
         if (e == cudaSuccess) e = cudaStreamSynchronize(d->compute);
         if (e != cudaSuccess) rc = fail(MXD_ERR_CUDA, cudaGetErrorString(e));
         c->d2h += n * 32;
-        cudaFree(d_buf);
+        cudaFreeAsync(d_buf, d->compute);
         return rc;
     }
     LockstepInput in;

@@ -20,12 +20,13 @@ def _tp(chunk: int, leaf: int, fanout: int):
 
 def _buf(data):
     """(address, nbytes, keepalive) of a bytes-like / numpy array without copying when possible."""
-    if isinstance(data, (bytes, bytearray)):
+    if isinstance(data, bytes):
+        # pointer to the bytes object's own storage (no copy; valid while `data` is referenced by the caller)
         n = len(data)
-        if isinstance(data, bytes):
-            keep = C.create_string_buffer(data, n) if n else C.create_string_buffer(1)
-        else:
-            keep = (C.c_char * max(n, 1)).from_buffer(data)
+        return (C.cast(C.c_char_p(data), C.c_void_p).value or 0), n, data
+    if isinstance(data, bytearray):
+        n = len(data)
+        keep = (C.c_char * max(n, 1)).from_buffer(data)
         return C.addressof(keep), n, keep
     mv = memoryview(data)
     if not mv.contiguous:
