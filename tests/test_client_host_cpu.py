@@ -142,3 +142,19 @@ def test_json_string_escaping_follows_encoding_json(tmp_path):
     def go_decode(b):   # Go replaces every undecodable byte by one U+FFFD (Python's "replace" merges truncated sequences)
         return "".join("\ufffd" if 0xDC80 <= ord(ch) <= 0xDCFF else ch for ch in b.decode("utf-8", "surrogateescape"))
     assert [b["name"] for b in m["blobs"]] == [go_decode(n) for n in sorted(names)]
+
+
+def test_manifest_parser_handles_escapes_and_rejects_garbage(tmp_path):
+    reg = client.LocalRegistry(str(tmp_path / "reg"))
+    # \\uXXXX escapes (incl. a surrogate pair), nested unknown fields, numbers with exponents are tolerated on input
+    text = ('{"schemaVersion": 1, "unknown": {"a": [1, 2.5e3, true, null]}, "config": {"name": "c\\u00e9\\ud83d\\ude00.yaml", '
+            '"modified": "2024-01-01T00:00:00Z"}, "blobs": [{"name": "w\\tx", "size": 7, "modified": "2024-01-01T00:00:00Z"}]}')
+    reg.put_manifest("r", "v", text)
+    out = reg.get_manifest_json("r", "v")
+    assert out == ('{"schemaVersion":1,"config":{"name":"cé😀.yaml","modified":"2024-01-01T00:00:00Z"},'
+                   '"blobs":[{"name":"w\\tx","size":7,"modified":"2024-01-01T00:00:00Z"}]}')
+    assert json.loads(out)["config"]["name"] == "cé😀.yaml"
+    for bad in ('', '[]', '{"config": 5}', '{"blobs": [1]}', '{"a": "unterminated}', '{"a": 1,}', '{' * 100):
+        with pytest.raises(modelx_b200.MxdError) as ei:
+            reg.put_manifest("r", "bad", bad)
+        assert ei.value.status == N.MXC_ERR_MANIFEST, bad
