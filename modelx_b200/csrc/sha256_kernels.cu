@@ -422,7 +422,7 @@ __global__ void k_gen_fill(uint64_t* __restrict__ dst, uint64_t first_word, uint
 // Occupancy: 24 warps per SM at 80 registers is the default (16..24 warps measure the same, 1.01 TB/s); 32 warps
 // at 63 registers is 11 % slower (profiles/r01_quick_bench_v3.txt).  MXD_TUNE_MINB=8 keeps the 32-warp build
 // selectable for A/B profiling.
-static int g_minb = [] { const char* e = getenv("MXD_TUNE_MINB"); return (e && atoi(e) == 8) ? 8 : 6; }();
+static int g_minb = [] { const char* e = getenv("MXD_TUNE_MINB"); const int v = e ? atoi(e) : 6; return (v == 8 || v == 4) ? v : 6; }();
 
 static long g_coop_max = [] { const char* e = getenv("MXD_TUNE_COOP"); return e ? atol(e) : 32768L; }();
 
@@ -437,8 +437,9 @@ cudaError_t launch_sha256(const MsgJob& job, cudaStream_t stream) {
         k_sha256_chains_coop<<<(unsigned)cblocks, 64, 0, stream>>>(job);
         return cudaGetLastError();
     }
-    if (g_minb == 8) k_sha256_lanes<16><<<(unsigned)blocks, kThreads, 0, stream>>>(job);
-    else             k_sha256_lanes<12><<<(unsigned)blocks, kThreads, 0, stream>>>(job);
+    if (g_minb == 8)      k_sha256_lanes<16><<<(unsigned)blocks, kThreads, 0, stream>>>(job);
+    else if (g_minb == 4) k_sha256_lanes<8><<<(unsigned)blocks, kThreads, 0, stream>>>(job);
+    else                  k_sha256_lanes<12><<<(unsigned)blocks, kThreads, 0, stream>>>(job);
     return cudaGetLastError();
 }
 
