@@ -57,6 +57,7 @@ typedef struct {
 /* Environment knobs (read once, at mxd_open / first launch):
  *   MXD_RING_BYTES      pinned + device ring size per device in bytes (overrides the ring_bytes argument)
  *   MXD_STAGE_THREADS   threads per device that fill ring slots from files / pageable memory (default min(16, cpus/devices))
+ *   MXD_STAGE_PIECE     bytes each filler thread reads at a time (default 4 MiB)
  *   MXD_NO_NUMA_BIND    set to disable binding pinned allocations and filler threads to the device's local CPUs
  *   MXD_TUNE_COOP       largest launch (in messages) that uses the two-warp cooperative kernel (default 32768, 0 = never)
  *   MXD_TUNE_MINB=8     select the 63-register build of the lanes kernel (A/B profiling only) */

@@ -337,7 +337,7 @@ struct Source {
 int source_stage(const Source& s, uint64_t off, uint64_t n, uint8_t* dst, const uint8_t** from, StagePool* pool = nullptr) {
     if (s.fd < 0 && s.pinned) { *from = s.mem + off; return MXD_OK; }
     *from = dst;
-    constexpr uint64_t kPiece = 4ull << 20;
+    static const uint64_t kPiece = [] { const char* e = getenv("MXD_STAGE_PIECE"); uint64_t v = e ? strtoull(e, nullptr, 10) : 0; return v >= 4096 ? v : (4ull << 20); }();
     const int pieces = (int)((n + kPiece - 1) / kPiece);
     std::atomic<int> err{0};
     auto fill = [&](int i) {
