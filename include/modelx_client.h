@@ -74,6 +74,14 @@ int mxc_blob_digest_path(const char* repository, const char* digest, char** path
  * -> JSON {"manifest":{...},"blobs":[{"name":..,"status":..}]}. */
 int mxc_push_local(mxd_ctx* ctx, const char* basedir, const char* configfile, const char* basepath,
                    const char* repository, const char* version, int verify, char** report_json);
+/* The read-once, tree-keyed push (NEW, not wire compatible with stock modelx clients): every blob is
+ * read from disk once -- the bytes stream through the pinned ring to the GPU (modelx.tree.v1 digest) and, in the
+ * same pass, into the store (mxd_tree_digest_file_tee) -- and is stored under its tree root:
+ * Descriptor.Digest = "sha256:<root>", Descriptor.Annotations["modelx.digest"] =
+ * "tree.v1;leaf=16384;fanout=8;chunk=8388608;chunks=<n>".  mxc_pull_check / mxc_pull_local recognise the annotation
+ * and verify local files with the tree digest.  Same report shape as mxc_push_local. */
+int mxc_push_local_tree(mxd_ctx* ctx, const char* basedir, const char* configfile, const char* basepath,
+                        const char* repository, const char* version, char** report_json);
 /* Client.Pull against the same store (pull.go:19-39, pullFile :111-143): check, then copy what is
  * missing or different out of the store with the descriptor's permission bits.
  * -> JSON array [{"name":..,"status":"already exists"|"empty"|"done"}]. */

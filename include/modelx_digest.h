@@ -126,6 +126,15 @@ int mxd_tree_digest(mxd_ctx*, const void* data /*host or device*/, uint64_t size
                     uint8_t* chunk_digests /*nchunks*32, may be NULL*/, uint64_t* nchunks, uint8_t root[32]);
 int mxd_tree_digest_file(mxd_ctx*, const char* path, const mxd_tree_params* tp,
                          uint8_t* chunk_digests, uint64_t cap_chunks, uint64_t* nchunks, uint64_t* size, uint8_t root[32]);
+/* Read-once form: the same digest, and every byte that streams through the pinned ring is also
+ * handed to `sink` (e.g. a part uploader or a store writer), so the file is read from disk once instead of once to
+ * hash and once to upload (push.go:160 then extension_s3.go:71-82).  The sink is called with disjoint pieces
+ * (<= 4 MiB) that together cover [0, size), possibly concurrently from several threads and in any order; the data
+ * pointer is only valid during the call.  A non-zero return aborts the digest with MXD_ERR_IO. */
+typedef int (*mxd_sink_fn)(void* user, uint64_t offset, const void* data, uint64_t nbytes);
+int mxd_tree_digest_file_tee(mxd_ctx*, const char* path, const mxd_tree_params* tp, uint8_t* chunk_digests,
+                             uint64_t cap_chunks, uint64_t* nchunks, uint64_t* size, uint8_t root[32],
+                             mxd_sink_fn sink, void* user);
 /* Sharded form (one process per GPU): chunk digests of a piece that starts on a chunk boundary... */
 int mxd_tree_chunks(mxd_ctx*, const void* piece /*host or device*/, uint64_t nbytes, const mxd_tree_params* tp,
                     uint8_t* chunk_digests /*max(1, ceil(nbytes/chunk))*32*/);

@@ -35,6 +35,9 @@ class TreeParams(C.Structure):
     _fields_ = [("chunk", C.c_uint64), ("leaf", C.c_uint64), ("fanout", C.c_uint32), ("reserved", C.c_uint32)]
 
 
+SINK_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64)
+
+
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("bytes_hashed", C.c_uint64), ("h2d_bytes", C.c_uint64),
                 ("d2h_bytes", C.c_uint64), ("reserved", C.c_uint64 * 4)]
@@ -73,6 +76,7 @@ PROTOTYPES = {
     "mxd_tree_shape": (C.c_int, [C.c_uint64, C.POINTER(TreeParams), u64p, C.c_int, C.POINTER(C.c_int)]),
     "mxd_tree_digest": (C.c_int, [vp, vp, C.c_uint64, C.POINTER(TreeParams), u8p, u64p, u8p]),
     "mxd_tree_digest_file": (C.c_int, [vp, C.c_char_p, C.POINTER(TreeParams), u8p, C.c_uint64, u64p, u64p, u8p]),
+    "mxd_tree_digest_file_tee": (C.c_int, [vp, C.c_char_p, C.POINTER(TreeParams), u8p, C.c_uint64, u64p, u64p, u8p, vp, vp]),
     "mxd_tree_chunks": (C.c_int, [vp, vp, C.c_uint64, C.POINTER(TreeParams), u8p]),
     "mxd_tree_finish": (C.c_int, [vp, u8p, C.c_uint64, C.c_uint64, C.POINTER(TreeParams), u8p]),
     "mxd_calc_parts": (C.c_int, [C.c_int64, C.c_int64, C.POINTER(Part)]),
@@ -106,6 +110,7 @@ PROTOTYPES.update({
     "mxc_fs_get_manifest": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p)]),
     "mxc_blob_digest_path": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p)]),
     "mxc_push_local": (C.c_int, [vp, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "mxc_push_local_tree": (C.c_int, [vp, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p)]),
     "mxc_pull_local": (C.c_int, [vp, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p)]),
 })
 

@@ -98,6 +98,19 @@ class Client:
         rep["manifest_json"] = text[len('{"manifest":'):text.rindex(',"blobs":[')]
         return rep
 
+    def push_tree(self, registry: LocalRegistry, repository: str, version: str, basedir: str,
+                  configfile: str = "modelx.yaml") -> dict:
+        """Read-once, tree-keyed push: each blob streams once through the pinned ring to the GPU
+        (modelx.tree.v1) and into the store, and is stored under its tree root."""
+        out = C.c_void_p()
+        N.check(self._lib.mxc_push_local_tree(self.engine.handle, basedir.encode(), configfile.encode(),
+                                              registry.basepath.encode(), repository.encode(), version.encode(),
+                                              C.byref(out)), "mxc_push_local_tree")
+        text = _take(self._lib, out)
+        rep = json.loads(text)
+        rep["manifest_json"] = text[len('{"manifest":'):text.rindex(',"blobs":[')]
+        return rep
+
     def pull(self, registry: LocalRegistry, repository: str, version: str, into: str) -> list:
         """Client.Pull (pull.go:19-39) against the in-process FS store."""
         out = C.c_void_p()

@@ -513,7 +513,15 @@ int read_file(const std::string& path, std::string* out) {
     return MXD_OK;
 }
 
-// pullFile's check, pull.go:111-136, for a list of descriptors, hashing all present files in one batch
+const char* kTreeMode = "tree.v1";
+const char* kTreeAnnotation = "modelx.digest";
+bool is_tree_keyed(const Descriptor& d) {
+    auto it = d.annotations.find(kTreeAnnotation);
+    return it != d.annotations.end() && it->second.compare(0, strlen(kTreeMode), kTreeMode) == 0;
+}
+
+// pullFile's check, pull.go:111-136, for a list of descriptors.  Whole-file digests of all present files are one
+// GPU batch; descriptors annotated as tree-keyed (mxc_push_local_tree) are checked with the tree digest instead.
 struct PullState { std::string name, digest, state; };
 int pull_check(mxd_ctx* ctx, const std::string& basedir, const std::vector<Descriptor>& descs, std::vector<PullState>* out) {
     std::vector<size_t> present;
@@ -528,7 +536,14 @@ int pull_check(mxd_ctx* ctx, const std::string& basedir, const std::vector<Descr
         if (stat(p.c_str(), &st) == 0) {
             // os.Open succeeds on a directory and digest.FromReader then fails with EISDIR (pull.go:116-119)
             if (S_ISDIR(st.st_mode)) return fail(MXD_ERR_IO, "read " + p + ": is a directory");
-            present.push_back(i); paths.push_back(p);
+            if (is_tree_keyed(d)) {
+                uint8_t root[32]; uint64_t nch = 0, sz = 0;
+                int rc = mxd_tree_digest_file(ctx, p.c_str(), nullptr, nullptr, 0, &nch, &sz, root);
+                if (rc != MXD_OK) return fail(rc, std::string("tree digest: ") + mxd_last_error());
+                (*out)[i].state = (digest_str(root) == d.digest) ? "already exists" : "differs";
+            } else {
+                present.push_back(i); paths.push_back(p);
+            }
         } else if (errno != ENOENT && errno != ENOTDIR) {
             return fail_errno("open " + p);                                      // pull.go:125-127
         }
@@ -541,7 +556,12 @@ int pull_check(mxd_ctx* ctx, const std::string& basedir, const std::vector<Descr
         for (size_t k = 0; k < present.size(); ++k)                           // pull.go:120 string equality
             (*out)[present[k]].state = (digest_str(&got[32 * k]) == descs[present[k]].digest) ? "already exists" : "differs";
     }
-    for (auto& s : *out) if (s.state != "already exists" && s.digest == kEmptyFileDigest) s.state = "empty";   // pull.go:134-136
+    for (size_t i = 0; i < descs.size(); ++i) {
+        PullState& s = (*out)[i];
+        if (s.state == "already exists") continue;
+        const bool empty = is_tree_keyed(descs[i]) ? descs[i].size == 0 : s.digest == kEmptyFileDigest;   // pull.go:134-136
+        if (empty) s.state = "empty";
+    }
     return MXD_OK;
 }
 
@@ -668,6 +688,79 @@ int mxc_push_local(mxd_ctx* ctx, const char* basedir, const char* configfile, co
     blobs += ']';
     const std::string mj = json_manifest(m);
     rc = fs_put_file(basepath, manifest_path(repository, version), kMediaTypeModelManifestJson, (int64_t)mj.size(), nullptr, &mj);  // push.go:57-64
+    if (rc != MXD_OK) return rc;
+    *report_json = dup_out("{\"manifest\":" + mj + ",\"blobs\":" + blobs + "}");
+    return MXD_OK;
+}
+
+static int pwrite_sink(void* user, uint64_t off, const void* data, uint64_t n) {
+    const int fd = *static_cast<int*>(user);
+    const char* p = static_cast<const char*>(data);
+    uint64_t done = 0;
+    while (done < n) {
+        ssize_t w = pwrite(fd, p + done, n - done, (off_t)(off + done));
+        if (w < 0) { if (errno == EINTR) continue; return 1; }
+        done += (uint64_t)w;
+    }
+    return 0;
+}
+
+int mxc_push_local_tree(mxd_ctx* ctx, const char* basedir, const char* configfile, const char* basepath,
+                        const char* repository, const char* version, char** report_json) {
+    if (!ctx || !basedir || !configfile || !basepath || !repository || !version || !report_json)
+        return fail(MXD_ERR_INVALID, "push_local_tree: null argument");
+    Manifest m;
+    int rc = parse_manifest(basedir, configfile, &m);
+    if (rc != MXD_OK) return rc;
+    if (m.config.name.empty()) return fail(MXD_ERR_IO, "stat " + join(basedir, configfile) + ": no such file or directory");
+    std::vector<Descriptor*> all;
+    for (auto& b : m.blobs) {
+        if (b.mediaType == kMediaTypeModelDirectoryTarGz)
+            return fail(MXC_ERR_UNSUPPORTED, "directory blob '" + b.name + "': tar+gzip is outside the digest path (DESIGN.md section 8)");
+        all.push_back(&b);
+    }
+    all.push_back(&m.config);
+    const std::string incoming_dir = join(join(join(basepath, repository), "blobs"), "sha256");
+    rc = mkdir_all(incoming_dir, 0755);
+    if (rc != MXD_OK) return rc;
+    std::string blobs = "[";
+    for (size_t i = 0; i < all.size(); ++i) {
+        Descriptor& d = *all[i];
+        const std::string src = join(basedir, d.name);
+        rc = push_file_fill(src, &d);
+        if (rc != MXD_OK) return rc;
+        const std::string tmp = join(incoming_dir, ".incoming-" + std::to_string((long)getpid()) + "-" + std::to_string(i));
+        int fd = open(tmp.c_str(), O_WRONLY | O_CREAT | O_TRUNC | O_CLOEXEC, 0644);
+        if (fd < 0) return fail_errno("open " + tmp);
+        uint8_t root[32]; uint64_t nch = 0, sz = 0;
+        rc = mxd_tree_digest_file_tee(ctx, src.c_str(), nullptr, nullptr, 0, &nch, &sz, root, pwrite_sink, &fd);   // one read: GPU + store
+        close(fd);
+        if (rc != MXD_OK) { unlink(tmp.c_str()); return fail(rc, std::string("tree digest: ") + mxd_last_error()); }
+        d.digest = digest_str(root);
+        d.annotations[kTreeAnnotation] = std::string(kTreeMode) + ";leaf=16384;fanout=8;chunk=8388608;chunks=" + std::to_string(nch);
+        std::string status, rel;
+        rc = blob_digest_path(repository, d.digest, &rel);
+        if (rc != MXD_OK) { unlink(tmp.c_str()); return rc; }
+        if (sz == 0) { unlink(tmp.c_str()); status = "empty"; }                   // like EmptyFileDigiest: nothing to upload
+        else {
+            const int ex = fs_exists(basepath, rel);
+            if (ex < 0) { unlink(tmp.c_str()); return ex; }
+            if (ex) { unlink(tmp.c_str()); status = "exists"; }
+            else {
+                const std::string datafile = join(basepath, rel);
+                rc = write_file(datafile + ".meta", meta_json("application/octet-stream", (int64_t)sz), 0644);
+                if (rc == MXD_OK && rename(tmp.c_str(), datafile.c_str()) != 0) rc = fail_errno("rename " + tmp);
+                if (rc != MXD_OK) { unlink(tmp.c_str()); return rc; }
+                status = "done";
+            }
+        }
+        if (i) blobs += ',';
+        blobs += "{\"name\":"; json_string(blobs, d.name); blobs += ",\"status\":"; json_string(blobs, status);
+        blobs += ",\"digest\":"; json_string(blobs, d.digest); blobs += '}';
+    }
+    blobs += ']';
+    const std::string mj = json_manifest(m);
+    rc = fs_put_file(basepath, manifest_path(repository, version), kMediaTypeModelManifestJson, (int64_t)mj.size(), nullptr, &mj);
     if (rc != MXD_OK) return rc;
     *report_json = dup_out("{\"manifest\":" + mj + ",\"blobs\":" + blobs + "}");
     return MXD_OK;

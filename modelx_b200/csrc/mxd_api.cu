@@ -329,7 +329,24 @@ struct Source {
     bool pinned = false;
     int fd = -1;                   // file source
     uint64_t base = 0;             // offset of this source's byte 0 inside the file
+    mxd_sink_fn sink = nullptr;    // optional tee: every streamed byte is also handed to this callback
+    void* sink_user = nullptr;
+    uint64_t sink_base = 0;        // logical offset of this source's byte 0 for the sink
 };
+
+// hand [off, off+n) (already staged at `data`) to the tee in <= 4 MiB pieces, in parallel on the pool
+int sink_slot(const Source& s, uint64_t off, uint64_t n, const uint8_t* data, StagePool* pool) {
+    if (!s.sink) return MXD_OK;
+    constexpr uint64_t kPiece = 4ull << 20;
+    const int pieces = (int)((n + kPiece - 1) / kPiece);
+    std::atomic<int> bad{0};
+    auto put = [&](int i) {
+        const uint64_t p0 = (uint64_t)i * kPiece, pn = std::min(kPiece, n - p0);
+        if (s.sink(s.sink_user, s.sink_base + off + p0, data + p0, pn) != 0) bad.store(1);
+    };
+    if (pool && pieces > 1) pool->parallel_for(pieces, put); else for (int i = 0; i < pieces; ++i) put(i);
+    return bad.load() ? fail(MXD_ERR_IO, "sink refused data") : MXD_OK;
+}
 
 // Fill `n` bytes at logical offset `off` of the source into pinned `dst`; returns the pointer the
 // H2D copy should read from (dst, or the caller's own memory when that is already pinned).
@@ -388,6 +405,8 @@ int stream_segments(mxd_ctx* c, DevState* d, const Source& src, uint64_t nbytes,
         rc = enqueue_segments(c, d_slot, n, seg, d_out + (off / seg) * 32, d->compute, /*leaf_level=*/true);
         if (rc != MXD_OK) return rc;
         MXD_CUDA(cudaEventRecord(d->ev_done[s], d->compute));
+        rc = sink_slot(src, off, n, from, d->pool);     // the tee runs while the copy engine and the SMs work on this slot
+        if (rc != MXD_OK) return rc;
         c->h2d += n;
         off += n;
     }
@@ -427,6 +446,7 @@ int host_tree_chunks_all(mxd_ctx* c, const Tree& t, const Source& src, uint64_t 
         const uint64_t b0 = c0 * chunk, b1 = std::min<uint64_t>(c1 * chunk, nbytes);
         Source piece = src;
         if (piece.fd >= 0) piece.base += b0; else piece.mem += b0;
+        piece.sink_base += b0;
         uint8_t* d_chunks = nullptr;
         cudaError_t e = cudaMallocAsync(&d_chunks, (c1 - c0) * 32, d->compute);
         if (e != cudaSuccess) { rcs[g] = MXD_ERR_CUDA; errs[g] = cudaGetErrorString(e); return; }
@@ -981,6 +1001,12 @@ int mxd_tree_digest(mxd_ctx* c, const void* data, uint64_t size, const mxd_tree_
 
 int mxd_tree_digest_file(mxd_ctx* c, const char* path, const mxd_tree_params* tp, uint8_t* chunk_digests,
                          uint64_t cap_chunks, uint64_t* nchunks_out, uint64_t* size_out, uint8_t root[32]) {
+    return mxd_tree_digest_file_tee(c, path, tp, chunk_digests, cap_chunks, nchunks_out, size_out, root, nullptr, nullptr);
+}
+
+int mxd_tree_digest_file_tee(mxd_ctx* c, const char* path, const mxd_tree_params* tp, uint8_t* chunk_digests,
+                             uint64_t cap_chunks, uint64_t* nchunks_out, uint64_t* size_out, uint8_t root[32],
+                             mxd_sink_fn sink, void* user) {
     Tree t;
     if (!c || !path || !tree_resolve(tp, &t) || !root) return fail(MXD_ERR_INVALID, "tree_digest_file: bad arguments");
     int fd = open(path, O_RDONLY | O_CLOEXEC);
@@ -995,7 +1021,7 @@ int mxd_tree_digest_file(mxd_ctx* c, const char* path, const mxd_tree_params* tp
     std::vector<uint8_t> tmp;
     uint8_t* chunks = chunk_digests;
     if (!chunks) { tmp.resize(nchunks * 32); chunks = tmp.data(); }
-    Source src; src.fd = fd;
+    Source src; src.fd = fd; src.sink = sink; src.sink_user = user;
     int rc = host_tree_chunks_all(c, t, src, size, chunks);
     close(fd);
     if (rc != MXD_OK) return rc;

@@ -251,6 +251,30 @@ class Engine:
         raw = bytes(chunks)
         return [raw[32 * i:32 * i + 32] for i in range(got.value)], bytes(root), sz.value
 
+    def tree_digest_file_tee(self, path: str, sink, chunk: int = DEFAULT_CHUNK, leaf: int = DEFAULT_LEAF,
+                             fanout: int = DEFAULT_FANOUT):
+        """Read-once digest: ``sink(offset, data: bytes)`` receives every piece that streams through the ring
+        (possibly from several threads, any order).  -> (chunk_digests, root, size)"""
+        import os
+        size = os.stat(path).st_size
+        nch = max(1, -(-size // chunk))
+        chunks = (C.c_uint8 * (32 * nch))()
+        got, sz = C.c_uint64(), C.c_uint64()
+        root = (C.c_uint8 * 32)()
+
+        def _cb(user, offset, data, nbytes):
+            try:
+                sink(offset, C.string_at(data, nbytes))
+                return 0
+            except Exception:
+                return 1
+        cb = N.SINK_FN(_cb)
+        N.check(self._lib.mxd_tree_digest_file_tee(self._ctx, path.encode(), _tp(chunk, leaf, fanout), chunks, nch,
+                                                   C.byref(got), C.byref(sz), root, C.cast(cb, C.c_void_p), None),
+                "mxd_tree_digest_file_tee")
+        raw = bytes(chunks)
+        return [raw[32 * i:32 * i + 32] for i in range(got.value)], bytes(root), sz.value
+
     def tree_chunks_ptr(self, ptr: int, n: int, chunk: int = DEFAULT_CHUNK, leaf: int = DEFAULT_LEAF,
                         fanout: int = DEFAULT_FANOUT) -> bytes:
         nch = max(1, -(-n // chunk))

@@ -163,3 +163,64 @@ def test_push_digest_cache_skips_unchanged_files(engine, tmp_path):
     assert engine.stats()["bytes_hashed"] - b0 < 5_000_000 + 8_000_100          # only README (+ the uncached full pass above)
     (d / ".modelx" / "digests.json").write_text("{broken")
     assert json.loads(cl.push_digest_json(str(d), use_cache=True)) == m          # unreadable cache = no cache
+
+
+def test_read_once_tree_keyed_push_and_pull(engine, oracle, tmp_path):
+    """every blob is read once -- the ring feeds the GPU (tree digest) and the store in the same pass --
+    and is stored under its tree root; pull verifies with the tree digest."""
+    d, files = _model(tmp_path, big=40_000_000)
+    reg = client.LocalRegistry(str(tmp_path / "reg"), engine)
+    cl = client.Client(engine)
+    b0 = engine.stats()["bytes_hashed"]
+    rep = cl.push_tree(reg, "library/llama", "v1", str(d))
+    hashed = engine.stats()["bytes_hashed"] - b0
+    total = sum(len(v) for v in files.values())
+    assert total <= hashed < total * 1.01 + 4096            # each byte went through the leaf kernel exactly once (+ tree levels)
+    base = tmp_path / "reg" / "library" / "llama" / "blobs" / "sha256"
+    m = json.loads(rep["manifest_json"])
+    for desc in m["blobs"] + [m["config"]]:
+        data = files[desc["name"]]
+        _, _, root = oracle.tree_digest(data, 8 << 20, 16 << 10, 8)
+        assert desc["digest"] == modelx_b200.digest_string(root)
+        nch = max(1, -(-len(data) // (8 << 20)))
+        assert desc["annotations"]["modelx.digest"] == f"tree.v1;leaf=16384;fanout=8;chunk=8388608;chunks={nch}"
+        hexd = desc["digest"].split(":")[1]
+        if len(data) == 0:
+            assert not (base / hexd).exists()
+        else:
+            assert (base / hexd).read_bytes() == data                       # written by the tee, not by a second read
+            assert json.loads((base / (hexd + ".meta")).read_text())["contentLength"] == len(data)
+    assert not [p for p in os.listdir(base) if p.startswith(".incoming")]  # temporaries renamed or removed
+    assert {b["name"]: b["status"] for b in rep["blobs"]}["empty.txt"] == "empty"
+    assert {b["status"] for b in cl.push_tree(reg, "library/llama", "v2", str(d))["blobs"]} == {"exists", "empty"}
+    into = tmp_path / "pulled"
+    res = {r["name"]: r["status"] for r in cl.pull(reg, "library/llama", "v1", str(into))}
+    assert set(res.values()) == {"done", "empty"}
+    for n, data in files.items():
+        assert (into / n).read_bytes() == data
+    assert set(r["status"] for r in cl.pull(reg, "library/llama", "v1", str(into))) == {"already exists"}
+    (into / "tokenizer.json").write_bytes(b"x")
+    assert {r["name"]: r["state"] for r in cl.pull_check(str(into), rep["manifest_json"])}["tokenizer.json"] == "differs"
+
+
+def test_tee_sink_sees_every_byte_once(engine, tmp_path):
+    size = 70_000_000 + 3
+    data = os.urandom(size)
+    p = tmp_path / "b.bin"
+    p.write_bytes(data)
+    got = bytearray(size)
+    seen = []
+    import threading
+    lock = threading.Lock()
+
+    def sink(offset, piece):
+        got[offset:offset + len(piece)] = piece
+        with lock:
+            seen.append((offset, len(piece)))
+
+    chunks, root, sz = engine.tree_digest_file_tee(str(p), sink)
+    assert sz == size and bytes(got) == data
+    seen.sort()
+    assert seen[0][0] == 0 and all(seen[i][0] + seen[i][1] == seen[i + 1][0] for i in range(len(seen) - 1))
+    assert seen[-1][0] + seen[-1][1] == size and max(l for _, l in seen) <= 4 << 20
+    assert (chunks, root) == engine.tree_digest_file(str(p))[:2]
