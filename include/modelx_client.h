@@ -59,7 +59,8 @@ int mxc_pull_check(mxd_ctx* ctx, const char* basedir, const char* manifest_json,
  *   <basepath>/<repository>/manifests/<reference>     types.Manifest JSON (store.go:67-69, store_fs.go:87-104)
  * verify != 0 is NEW behaviour: the stored bytes are re-hashed on the GPU and a
  * mismatch with `digest` removes the blob and returns MXC_ERR_DIGEST_INVALID; the reference stores
- * the body unverified (registry.go:144-164). */
+ * the body unverified (registry.go:144-164).  verify == 1: `digest` is the whole-file SHA-256;
+ * verify == 2: `digest` is a modelx.tree.v1 root (blobs pushed by mxc_push_local_tree). */
 int mxc_fs_put_blob(mxd_ctx* ctx, const char* basepath, const char* repository, const char* digest,
                     const char* content_type, const char* srcfile, int verify);
 int mxc_fs_exists_blob(const char* basepath, const char* repository, const char* digest); /* 1 / 0 / <0 */

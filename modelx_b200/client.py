@@ -42,10 +42,12 @@ class LocalRegistry:
         self._lib = N.load()
 
     def put_blob(self, repository: str, digest: str, srcfile: str, content_type: str = "application/octet-stream",
-                 verify: bool = False) -> None:
+                 verify=False) -> None:
+        """verify: False/0 (reference behaviour: store unverified), True/1 (whole-file digest), "tree"/2 (tree root)."""
         ctx = self.engine.handle if self.engine else None
+        mode = 2 if verify in ("tree", 2) else (1 if verify else 0)
         N.check(self._lib.mxc_fs_put_blob(ctx, self.basepath.encode(), repository.encode(), digest.encode(),
-                                          content_type.encode(), srcfile.encode(), 1 if verify else 0), "mxc_fs_put_blob")
+                                          content_type.encode(), srcfile.encode(), mode), "mxc_fs_put_blob")
 
     def exists_blob(self, repository: str, digest: str) -> bool:
         rc = self._lib.mxc_fs_exists_blob(self.basepath.encode(), repository.encode(), digest.encode())

@@ -482,7 +482,7 @@ int fs_exists(const std::string& basepath, const std::string& rel) {   // LocalF
     return fail_errno("stat " + join(basepath, rel));
 }
 int fs_put_blob(mxd_ctx* ctx, const std::string& basepath, const std::string& repo, const std::string& digest,
-                const std::string& content_type, const std::string& srcfile, bool verify) {
+                const std::string& content_type, const std::string& srcfile, int verify) {
     uint8_t want[32];
     if (mxd_digest_parse(digest.c_str(), want) != MXD_OK) return fail(MXC_ERR_DIGEST_INVALID, "digest invalid: " + digest);  // BlobDigestFun, registry.go:218-227
     if (content_type.empty()) return fail(MXD_ERR_INVALID, "content type invalid: empty");                                // registry.go:147-151
@@ -498,7 +498,13 @@ int fs_put_blob(mxd_ctx* ctx, const std::string& basepath, const std::string& re
         const std::string stored = join(basepath, rel);
         const char* p[1] = {stored.c_str()};
         uint8_t ok = 0;
-        rc = mxd_verify_files(ctx, p, want, 1, &ok);
+        if (verify == 2) {          // the key is a modelx.tree.v1 root (mxc_push_local_tree)
+            uint8_t root[32]; uint64_t nch = 0, sz = 0;
+            rc = mxd_tree_digest_file(ctx, stored.c_str(), nullptr, nullptr, 0, &nch, &sz, root);
+            ok = rc == MXD_OK && memcmp(root, want, 32) == 0;
+        } else {
+            rc = mxd_verify_files(ctx, p, want, 1, &ok);
+        }
         if (rc != MXD_OK) return fail(rc, std::string("verify: ") + mxd_last_error());
         if (!ok) { unlink(stored.c_str()); unlink((stored + ".meta").c_str()); return fail(MXC_ERR_DIGEST_INVALID, "digest invalid: " + digest); }
     }
@@ -624,7 +630,7 @@ int mxc_blob_digest_path(const char* repository, const char* digest, char** path
 int mxc_fs_put_blob(mxd_ctx* ctx, const char* basepath, const char* repository, const char* digest,
                     const char* content_type, const char* srcfile, int verify) {
     if (!basepath || !repository || !digest || !content_type || !srcfile) return fail(MXD_ERR_INVALID, "fs_put_blob: null argument");
-    return fs_put_blob(ctx, basepath, repository, digest, content_type, srcfile, verify != 0);
+    return fs_put_blob(ctx, basepath, repository, digest, content_type, srcfile, verify);
 }
 
 int mxc_fs_exists_blob(const char* basepath, const char* repository, const char* digest) {
@@ -676,7 +682,7 @@ int mxc_push_local(mxd_ctx* ctx, const char* basedir, const char* configfile, co
             if (ex) status = "exists";
             else {
                 // fallback upload through the server: Content-Type application/octet-stream (client/registry.go:109-120)
-                rc = fs_put_blob(ctx, basepath, repository, d.digest, "application/octet-stream", join(basedir, d.name), verify != 0);
+                rc = fs_put_blob(ctx, basepath, repository, d.digest, "application/octet-stream", join(basedir, d.name), verify ? 1 : 0);
                 if (rc != MXD_OK) return rc;
                 status = "done";
             }

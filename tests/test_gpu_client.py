@@ -141,6 +141,14 @@ def test_put_blob_verify_rejects_wrong_digest(engine, tmp_path):
     assert reg.exists_blob("library/m", good)
     reg.put_blob("library/m", bad, str(src), verify=False)       # reference behaviour: stored unverified
     assert reg.exists_blob("library/m", bad)
+    # tree-keyed blobs verify against the tree root
+    _, root = engine.tree_digest(src.read_bytes())
+    tree_key = modelx_b200.digest_string(root)
+    reg.put_blob("library/t", tree_key, str(src), verify="tree")
+    assert reg.exists_blob("library/t", tree_key)
+    with pytest.raises(modelx_b200.MxdError) as ei:
+        reg.put_blob("library/t", good, str(src), verify="tree")   # whole-file digest is not the tree root
+    assert ei.value.status == N.MXC_ERR_DIGEST_INVALID and not reg.exists_blob("library/t", good)
 
 
 def test_push_digest_cache_skips_unchanged_files(engine, tmp_path):
