@@ -343,7 +343,7 @@ def test_cancel_from_another_thread_mid_stream(oracle):
     """ctx cancel while a large pageable blob is streaming: the call returns MXD_ERR_CANCELED promptly
     (push.go:156-159 semantics) and the engine is usable again after reset."""
     import numpy as np
-    size = 3_000_000_000
+    size = 8_000_000_000          # >= 145 ms of streaming even at full PCIe rate; the cancel lands 20 ms in
     blob = np.zeros(size, dtype=np.uint8)
     blob[::4096] = 7
     with modelx_b200.Engine(devices=[0], ring_bytes=64 << 20) as eng:
@@ -359,7 +359,7 @@ def test_cancel_from_another_thread_mid_stream(oracle):
         t = threading.Thread(target=work)
         t.start()
         import time
-        time.sleep(0.05)
+        time.sleep(0.02)
         eng.cancel()
         t.join(timeout=60)
         assert not t.is_alive() and result["rc"] == -6
