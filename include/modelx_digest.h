@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MXD_ABI_VERSION 1
+#define MXD_ABI_VERSION 2
 
 typedef enum mxd_status {
     MXD_OK = 0,
@@ -38,7 +38,7 @@ typedef enum mxd_status {
     MXD_ERR_CUDA = -3,         /* a CUDA call failed; mxd_last_error() has the text (maps to INTERNAL, errors.go:65) */
     MXD_ERR_IO = -4,           /* open/read failed; errno preserved (reference returns the os error) */
     MXD_ERR_NOMEM = -5,
-    MXD_ERR_CANCELED = -6,     /* mxd_cancel() was called (reference: ctx cancel closes the fd, push.go:156-159) */
+    MXD_ERR_CANCELED = -6,     /* the call's operation was canceled (reference: ctx cancel closes the fd, push.go:156-159) */
     MXD_ERR_DIV_ZERO = -7      /* calcParts with 0 parts: the reference panics (extension_s3.go:100) */
 } mxd_status;
 
@@ -51,7 +51,9 @@ typedef struct {
     uint64_t kernel_launches;   /* SHA-256 / compare / generator kernels launched by this context */
     uint64_t bytes_hashed;      /* message bytes submitted to the SHA-256 kernel */
     uint64_t h2d_bytes, d2h_bytes;
-    uint64_t reserved[4];
+    uint64_t src_bytes_read;    /* bytes read from files / copied out of host buffers into the pinned ring (read-once accounting) */
+    uint64_t open_files;        /* files the digest service holds open right now (bounded, see MXD_MAX_OPEN_FILES) */
+    uint64_t reserved[2];
 } mxd_stats;
 
 /* Environment knobs (read once, at mxd_open / first launch):
@@ -59,8 +61,11 @@ typedef struct {
  *   MXD_STAGE_THREADS   threads per device that fill ring slots from files / pageable memory (default min(16, cpus/devices))
  *   MXD_STAGE_PIECE     bytes each filler thread reads at a time (default 4 MiB)
  *   MXD_NO_NUMA_BIND    set to disable binding pinned allocations and filler threads to the device's local CPUs
+ *   MXD_MAX_OPEN_FILES  files the whole-message digest service may hold open at once (default RLIMIT_NOFILE/2 - 32, capped at 4096)
  *   MXD_TUNE_COOP       largest launch (in messages) that uses the two-warp cooperative kernel (default 32768, 0 = never)
- *   MXD_TUNE_MINB=8     select the 63-register build of the lanes kernel (A/B profiling only) */
+ *   MXD_TUNE_MINB=8     select the 63-register build of the lanes kernel (A/B profiling only)
+ *   MXD_TUNE_LEAF=legacy        tree leaves through the generic kernel, every tree level its own launch (A/B profiling only)
+ *   MXD_TUNE_LEAF_SCHED=1       fused leaf kernel with a plain grid instead of the per-SM round schedule (A/B profiling only) */
 
 /* ---- lifecycle ------------------------------------------------------------------------- */
 /* devices/ndev: CUDA ordinals to drive from this process (ndev == 0: all visible devices).
@@ -68,14 +73,31 @@ typedef struct {
 int  mxd_open(mxd_ctx** out, const int* devices, int ndev, uint64_t ring_bytes);
 void mxd_close(mxd_ctx* ctx);
 int  mxd_device_count(const mxd_ctx* ctx);
-void mxd_cancel(mxd_ctx* ctx);              /* abort in-flight streaming calls with MXD_ERR_CANCELED */
-void mxd_reset_cancel(mxd_ctx* ctx);
+/* ---- operations: per-call cancellation ----------------------------------------------------
+ * The reference cancels ONE digest through that call's own context (push.go:150-159: ctx.Done closes the fd) and
+ * the first failing blob cancels its siblings through their shared context (progress/mbar.go:108-115).  An
+ * operation handle is that context: mxd_op_begin returns a handle that can be passed wherever an mxd_ctx* is
+ * accepted (it shares the devices, rings and digest service of its parent); mxd_cancel(op) makes every call made
+ * through THAT handle -- running or future -- return MXD_ERR_CANCELED and touches nobody else.  One operation per
+ * call gives push.go:150-159; one operation shared by the blobs of a Push gives mbar.go:108-115.
+ * mxd_cancel(root handle) aborts every call that is in flight on the context at that moment (process shutdown);
+ * it is not sticky: calls started afterwards run normally. */
+int  mxd_op_begin(mxd_ctx* parent, mxd_ctx** op);
+void mxd_op_end(mxd_ctx* op);               /* after the last call through it has returned */
+void mxd_cancel(mxd_ctx* handle);
+void mxd_reset_cancel(mxd_ctx* op);         /* un-cancel an operation handle (no effect on a root handle) */
+int  mxd_is_canceled(const mxd_ctx* op);
 int  mxd_get_stats(const mxd_ctx* ctx, mxd_stats* out);
 /* Live kernel timing for benchmarks: while enabled, every leaf-level SHA-256 launch (the launch
  * that reads blob bytes) is bracketed by CUDA events on its own stream.  mxd_prof_read waits for
  * them and returns the accumulated device time, launch count and message bytes, then clears. */
 int  mxd_prof_enable(mxd_ctx* ctx, int on);
 int  mxd_prof_read(mxd_ctx* ctx, double* kernel_ms, uint64_t* launches, uint64_t* bytes);
+/* Slot timeline of the streaming ring (overlap evidence without a system profiler): while enabled, every ring slot
+ * of the tree path records host fill time and CUDA events around its H2D copy and its kernel; mxd_trace_dump writes
+ * them as CSV (times in ms since the first record's copy start, per device) and clears the record. */
+int  mxd_trace_enable(mxd_ctx* ctx, int on);
+int  mxd_trace_dump(mxd_ctx* ctx, const char* csv_path);
 const char* mxd_strerror(int status);
 const char* mxd_last_error(void);           /* thread-local detail of the last failure on this thread */
 int  mxd_abi_version(void);
@@ -89,6 +111,28 @@ int mxd_sha256_batch(mxd_ctx*, const mxd_span* spans, uint64_t n, uint8_t* out /
 int mxd_sha256_file(mxd_ctx*, const char* path, uint8_t out[32], uint64_t* size);        /* Client.digest, push.go:149-161; pull.go:116 */
 int mxd_sha256_files(mxd_ctx*, const char* const* paths, uint64_t n, uint8_t* out /*n*32*/,
                      uint64_t* sizes /*n, may be NULL*/);                                /* Push/PullBlobs fan-out, push.go:36-52, pull.go:41-50 */
+/* The general form behind the calls above: one job per file, each with its own status, so one unreadable or
+ * canceled file does not fail its siblings.  A job may ask for the SHA-256 of several byte ranges of its file --
+ * e.g. {0,size} and every calcParts range (extension_s3.go:99-112) -- and may tee every byte of the file to a sink
+ * (a part uploader / store writer): the file is then read from disk ONCE, where the reference reads it once to hash
+ * (push.go:160) and once more to upload (extension_s3.go:71-82).  All jobs of a call, and all calls in flight from
+ * other threads, advance together as lanes of the same GPU rounds.  Sink contract: as mxd_sink_fn below. */
+typedef int (*mxd_sink_fn)(void* user, uint64_t offset, const void* data, uint64_t nbytes);
+typedef struct {
+    const char* path;
+    const mxd_part* ranges; uint64_t nranges;   /* nranges == 0: one digest of the whole file */
+    uint8_t* out;                               /* max(nranges, 1) * 32 bytes */
+    mxd_sink_fn sink; void* sink_user;          /* may be NULL */
+    uint64_t size;                              /* out: file size */
+    int status;                                 /* out: MXD_OK or this file's error */
+} mxd_file_job;
+int mxd_sha256_file_jobs(mxd_ctx*, mxd_file_job* jobs, uint64_t n);   /* returns MXD_OK or the first failing job's status */
+int mxd_sha256_file_ranges(mxd_ctx*, const char* path, const mxd_part* ranges, uint64_t n, uint8_t* out /*n*32*/,
+                           uint64_t* size, mxd_sink_fn sink, void* sink_user);
+/* Routing advice for callers that still own a CPU SHA-256 (the Go client's crypto/sha256): 1 when hashing this many
+ * blobs together on the GPU is expected to beat the reference's 3 goroutines on SHA-NI cores, else 0.  A single
+ * whole-file digest is one serial chain and never pays off; see INTEGRATION.md section 3 for the measured table. */
+int mxd_batch_pays_off(uint64_t n_blobs, uint64_t total_bytes, uint64_t max_blob_bytes);
 /* pull.go:115-123: "do I already have this blob?"  ok[i] = 1 iff SHA-256(span i) == want[i]. */
 int mxd_verify_batch(mxd_ctx*, const mxd_span* spans, const uint8_t* want /*n*32*/, uint64_t n, uint8_t* ok /*n*/);
 int mxd_verify_files(mxd_ctx*, const char* const* paths, const uint8_t* want /*n*32*/, uint64_t n, uint8_t* ok /*n*/);
@@ -99,7 +143,9 @@ int  mxd_hasher_new(mxd_ctx*, mxd_hasher** out);
 int  mxd_hasher_write(mxd_hasher*, const void* data, uint64_t n);
 int  mxd_hasher_sum(mxd_hasher*, uint8_t out[32]);
 int  mxd_hasher_reset(mxd_hasher*);
-uint64_t mxd_hasher_size(const mxd_hasher*);   /* bytes written so far */
+uint64_t mxd_hasher_size(const mxd_hasher*);        /* hash.Hash.Size(): 32 */
+uint64_t mxd_hasher_block_size(const mxd_hasher*);  /* hash.Hash.BlockSize(): 64 */
+uint64_t mxd_hasher_written(const mxd_hasher*);     /* bytes written so far */
 void mxd_hasher_free(mxd_hasher*);
 
 /* ---- chunked tree digest (new; what lets one blob use every lane and every GPU) -----------
@@ -131,7 +177,6 @@ int mxd_tree_digest_file(mxd_ctx*, const char* path, const mxd_tree_params* tp,
  * hash and once to upload (push.go:160 then extension_s3.go:71-82).  The sink is called with disjoint pieces
  * (<= 4 MiB) that together cover [0, size), possibly concurrently from several threads and in any order; the data
  * pointer is only valid during the call.  A non-zero return aborts the digest with MXD_ERR_IO. */
-typedef int (*mxd_sink_fn)(void* user, uint64_t offset, const void* data, uint64_t nbytes);
 int mxd_tree_digest_file_tee(mxd_ctx*, const char* path, const mxd_tree_params* tp, uint8_t* chunk_digests,
                              uint64_t cap_chunks, uint64_t* nchunks, uint64_t* size, uint8_t root[32],
                              mxd_sink_fn sink, void* user);

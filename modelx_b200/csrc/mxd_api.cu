@@ -1,47 +1,33 @@
-// C ABI of libmodelxdigest.so (include/modelx_digest.h): contexts, the pinned-host ring that
-// streams host/file data to the GPUs, tree assembly, and the integer split helpers.
-// Host side of the hot path of kubegems/modelx push/pull; each entry point cites the reference
-// call site it replaces in the header.  There is deliberately no CPU hashing in this file: if
-// CUDA is unavailable every digest call fails.
-#include "../../include/modelx_digest.h"
-#include "kernels.h"
+// C ABI of libmodelxdigest.so (include/modelx_digest.h): handles and operations, the pinned-host ring that
+// streams host/file data to the GPUs, tree assembly, device-resident forms and the integer split helpers.
+// Host side of the hot path of kubegems/modelx push/pull; each entry point cites the reference call site it
+// replaces in the header.  There is deliberately no CPU hashing in this library: if CUDA is unavailable every
+// digest call fails.
+#include "mxd_core.h"
 
-#include <algorithm>
-#include <atomic>
 #include <cerrno>
-#include <condition_variable>
-#include <functional>
 #include <cstdio>
 #include <cstdlib>
-#include <cstring>
 #include <fcntl.h>
 #include <fstream>
-#include <mutex>
-#include <sched.h>
-#include <string>
+#include <sys/resource.h>
 #include <sys/stat.h>
-#include <thread>
 #include <unistd.h>
-#include <vector>
+
+namespace mxdi {
+
+namespace {
+thread_local std::string g_last_error;
+}
+int fail(int status, const std::string& msg) { g_last_error = msg; return status; }
+const std::string& last_error() { return g_last_error; }
+
+const uint32_t kIVHost[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au, 0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
 
 namespace {
 
-thread_local std::string g_last_error;
-
-int fail(int status, const std::string& msg) {
-    g_last_error = msg;
-    return status;
-}
-
-#define MXD_CUDA(expr)                                                                              \
-    do {                                                                                            \
-        cudaError_t _e = (expr);                                                                    \
-        if (_e != cudaSuccess)                                                                      \
-            return fail(MXD_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));          \
-    } while (0)
-
 // MXD_DEBUG_TIMING=1: print host-side phase timings of the streaming calls to stderr (developer aid)
-static const bool g_dbg_timing = getenv("MXD_DEBUG_TIMING") != nullptr;
+const bool g_dbg_timing = getenv("MXD_DEBUG_TIMING") != nullptr;
 struct PhaseTimer {
     const char* what; timespec t0;
     explicit PhaseTimer(const char* w) : what(w) { if (g_dbg_timing) clock_gettime(CLOCK_MONOTONIC, &t0); }
@@ -51,10 +37,11 @@ struct PhaseTimer {
         fprintf(stderr, "[mxd] %-28s %9.3f ms\n", what, (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6);
     }
 };
+double now_ms() { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e3 + t.tv_nsec * 1e-6; }
 
 constexpr uint64_t kDefaultRingBytes = 256ull << 20;
-const uint32_t kIVHost[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au, 0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
-constexpr int kSlots = 4;
+
+}  // namespace
 
 // ---- NUMA locality ------------------------------------------------------------------------------------
 // On an 8-GPU HGX board four GPUs hang off each CPU socket.  Pinned buffers that end up on the other
@@ -83,228 +70,61 @@ bool device_local_cpus(int ordinal, cpu_set_t* set) {
     return count > 0;
 }
 
-// Scoped: run the enclosed allocations (first touch + pin) on the device's local CPUs, then restore.
-struct LocalCpuScope {
-    cpu_set_t old; bool active = false;
-    explicit LocalCpuScope(int ordinal) {
-        cpu_set_t want;
-        if (getenv("MXD_NO_NUMA_BIND") || !device_local_cpus(ordinal, &want)) return;
-        if (sched_getaffinity(0, sizeof old, &old) != 0) return;
-        cpu_set_t both; CPU_AND(&both, &old, &want);            // stay inside whatever the container allows
-        if (CPU_COUNT(&both) == 0) return;
-        active = sched_setaffinity(0, sizeof both, &both) == 0;
-    }
-    ~LocalCpuScope() { if (active) sched_setaffinity(0, sizeof old, &old); }
-};
+LocalCpuScope::LocalCpuScope(int ordinal) {
+    cpu_set_t want;
+    if (getenv("MXD_NO_NUMA_BIND") || !device_local_cpus(ordinal, &want)) return;
+    if (sched_getaffinity(0, sizeof old, &old) != 0) return;
+    cpu_set_t both; CPU_AND(&both, &old, &want);            // stay inside whatever the container allows
+    if (CPU_COUNT(&both) == 0) return;
+    active = sched_setaffinity(0, sizeof both, &both) == 0;
+}
+LocalCpuScope::~LocalCpuScope() { if (active) sched_setaffinity(0, sizeof old, &old); }
 
-// Small persistent worker pool that fills pinned ring slots (pread / memcpy) in parallel: one
-// thread reads the page cache at 2-4 GB/s, far below the 55 GB/s a PCIe Gen5 x16 link moves.
-class StagePool {
-public:
-    explicit StagePool(int nthreads) {
-        for (int i = 0; i < nthreads; ++i) workers_.emplace_back([this] { run(); });
+// ---- StagePool -------------------------------------------------------------------------------------------
+StagePool::StagePool(int nthreads) {
+    for (int i = 0; i < nthreads; ++i) workers_.emplace_back([this] { run(); });
+}
+StagePool::~StagePool() {
+    { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+    cv_.notify_all();
+    for (auto& t : workers_) t.join();
+}
+void StagePool::parallel_for(int n, const std::function<void(int)>& fn) {
+    if (n <= 0) return;
+    if (n == 1 || workers_.empty()) { for (int i = 0; i < n; ++i) fn(i); return; }
+    Batch b; b.fn = &fn; b.n = n; b.next = 0; b.done = 0;
+    { std::lock_guard<std::mutex> lk(mu_); queue_.push_back(&b); }
+    cv_.notify_all();
+    for (;;) {  // the caller works too
+        int i = b.next.fetch_add(1);
+        if (i >= n) break;
+        fn(i);
+        b.done.fetch_add(1);
     }
-    ~StagePool() {
-        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
-        cv_.notify_all();
-        for (auto& t : workers_) t.join();
-    }
-    // run fn(i) for i in [0, n) on the pool plus the calling thread; returns when all are done
-    void parallel_for(int n, const std::function<void(int)>& fn) {
-        if (n <= 0) return;
-        if (n == 1 || workers_.empty()) { for (int i = 0; i < n; ++i) fn(i); return; }
-        Batch b; b.fn = &fn; b.n = n; b.next = 0; b.done = 0;
-        { std::lock_guard<std::mutex> lk(mu_); queue_.push_back(&b); }
-        cv_.notify_all();
-        for (;;) {  // the caller works too
-            int i = b.next.fetch_add(1);
-            if (i >= n) break;
-            fn(i);
-            b.done.fetch_add(1);
-        }
-        std::unique_lock<std::mutex> lk(mu_);
-        for (auto it = queue_.begin(); it != queue_.end(); ++it) if (*it == &b) { queue_.erase(it); break; }
-        done_cv_.wait(lk, [&] { return b.done.load() >= n && b.active == 0; });
-    }
-private:
-    struct Batch { const std::function<void(int)>* fn; int n; std::atomic<int> next, done; int active = 0; };
-    void run() {
-        std::unique_lock<std::mutex> lk(mu_);
+    std::unique_lock<std::mutex> lk(mu_);
+    for (auto it = queue_.begin(); it != queue_.end(); ++it) if (*it == &b) { queue_.erase(it); break; }
+    done_cv_.wait(lk, [&] { return b.done.load() >= n && b.active == 0; });
+}
+void StagePool::run() {
+    std::unique_lock<std::mutex> lk(mu_);
+    for (;;) {
+        cv_.wait(lk, [&] { return stop_ || !queue_.empty(); });
+        if (stop_) return;
+        Batch* b = queue_.front();
+        if (b->next.load() >= b->n) { queue_.erase(queue_.begin()); continue; }
+        b->active++;
+        lk.unlock();
         for (;;) {
-            cv_.wait(lk, [&] { return stop_ || !queue_.empty(); });
-            if (stop_) return;
-            Batch* b = queue_.front();
-            if (b->next.load() >= b->n) { queue_.erase(queue_.begin()); continue; }
-            b->active++;
-            lk.unlock();
-            for (;;) {
-                int i = b->next.fetch_add(1);
-                if (i >= b->n) break;
-                (*b->fn)(i);
-                b->done.fetch_add(1);
-            }
-            lk.lock();
-            b->active--;
-            done_cv_.notify_all();
+            int i = b->next.fetch_add(1);
+            if (i >= b->n) break;
+            (*b->fn)(i);
+            b->done.fetch_add(1);
         }
+        lk.lock();
+        b->active--;
+        done_cv_.notify_all();
     }
-    std::vector<std::thread> workers_;
-    std::vector<Batch*> queue_;
-    std::mutex mu_;
-    std::condition_variable cv_, done_cv_;
-    bool stop_ = false;
-};
-
-struct DevState {
-    int ordinal = -1;
-    cudaStream_t compute = nullptr, copy = nullptr;
-    uint64_t slot_bytes = 0;
-    uint8_t* h_ring = nullptr;  // kSlots * slot_bytes, pinned
-    uint8_t* d_ring = nullptr;  // kSlots * slot_bytes
-    cudaEvent_t ev_copied[kSlots] = {}, ev_done[kSlots] = {};
-    std::mutex mu;               // one streaming operation per device at a time
-    StagePool* pool = nullptr;   // slot fillers for this device
-    uint8_t* h_desc = nullptr;   // pinned per-round descriptors of lock-step batches (grown on demand, under mu)
-    uint64_t h_desc_bytes = 0;
-};
-
-}  // namespace
-
-struct mxd_ctx {
-    std::vector<DevState*> devs;
-    std::atomic<uint64_t> launches{0}, bytes_hashed{0}, h2d{0}, d2h{0};
-    std::atomic<int> canceled{0};
-    std::atomic<uint32_t> rr{0};  // round-robin device pick for single-device calls
-    // live timing of leaf-level launches (mxd_prof_*)
-    std::atomic<int> prof_on{0};
-    std::mutex prof_mu;
-    struct ProfRec { cudaEvent_t a, b; uint64_t bytes; int ordinal; };
-    std::vector<ProfRec> prof;
-};
-
-namespace {
-
-struct DeviceGuard {
-    int prev = -1;
-    explicit DeviceGuard(int ordinal) { cudaGetDevice(&prev); cudaSetDevice(ordinal); }
-    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
-};
-
-// Resolved tree parameters: chunk = leaf * fanout^klevel.
-struct Tree {
-    uint64_t chunk = 8ull << 20, leaf = 16ull << 10, fanout = 8;
-    int klevel = 3;
-};
-
-bool tree_resolve(const mxd_tree_params* tp, Tree* t) {
-    if (tp) { t->chunk = tp->chunk; t->leaf = tp->leaf; t->fanout = tp->fanout; }
-    if (t->leaf < 64 || (t->leaf % 64) != 0 || t->fanout < 2 || t->chunk < t->leaf) return false;
-    if (tp && tp->reserved != 0) return false;
-    uint64_t span = t->leaf;
-    int k = 0;
-    while (span < t->chunk) {
-        if (span > t->chunk / t->fanout) return false;   // overflow / not a power
-        span *= t->fanout; ++k;
-    }
-    if (span != t->chunk || k < 1) return false;
-    t->klevel = k;
-    return true;
 }
-
-// ---- kernel enqueue helpers ------------------------------------------------------------------
-int enqueue_segments(mxd_ctx* c, const uint8_t* d_data, uint64_t nbytes, uint64_t seg, uint8_t* d_out, cudaStream_t st,
-                     bool leaf_level = false) {
-    mxd_ctx::ProfRec rec{};
-    bool prof = leaf_level && c->prof_on.load();
-    if (prof) { std::lock_guard<std::mutex> lk(c->prof_mu); if (c->prof.size() >= (1u << 16)) prof = false; }   // bounded
-    if (prof) {
-        cudaGetDevice(&rec.ordinal);
-        MXD_CUDA(cudaEventCreate(&rec.a));
-        MXD_CUDA(cudaEventCreate(&rec.b));
-        rec.bytes = nbytes;
-        MXD_CUDA(cudaEventRecord(rec.a, st));
-    }
-    mxd::MsgJob j{};
-    j.base = d_data; j.nbytes = nbytes; j.seg = seg;
-    j.nmsg = nbytes ? (nbytes + seg - 1) / seg : 1;
-    j.out = d_out; j.finalize = 1; j.one = 1;
-    if (j.base == nullptr) {  // empty message: any non-null base keeps the kernel in segment mode
-        j.base = reinterpret_cast<const uint8_t*>(d_out);
-    }
-    MXD_CUDA(mxd::launch_sha256(j, st));
-    c->launches++; c->bytes_hashed += nbytes;
-    if (prof) {
-        MXD_CUDA(cudaEventRecord(rec.b, st));
-        std::lock_guard<std::mutex> lk(c->prof_mu);
-        c->prof.push_back(rec);
-    }
-    return MXD_OK;
-}
-
-// digests of one tree level -> the next: groups of `fanout` digests
-int enqueue_level(mxd_ctx* c, const uint8_t* d_in, uint64_t n, uint64_t fanout, uint8_t* d_out, cudaStream_t st) {
-    return enqueue_segments(c, d_in, n * 32, 32 * fanout, d_out, st);
-}
-
-// leaf digests (level 0, n0 of them in d_leaves, clobbered as scratch) -> chunk digests (level k)
-int enqueue_leaves_to_chunks(mxd_ctx* c, const Tree& t, uint8_t* d_leaves, uint64_t n0, uint8_t* d_chunks, cudaStream_t st) {
-    // ping-pong between the leaf buffer and one scratch buffer of the level-1 size
-    uint64_t n = n0;
-    const uint64_t n1 = (n0 + t.fanout - 1) / t.fanout;
-    uint8_t* scratch = nullptr;
-    if (t.klevel > 1) MXD_CUDA(cudaMallocAsync(&scratch, n1 * 32, st));
-    uint8_t* cur = d_leaves;
-    int rc = MXD_OK;
-    for (int lv = 1; lv <= t.klevel && rc == MXD_OK; ++lv) {
-        const uint64_t nn = (n + t.fanout - 1) / t.fanout;
-        uint8_t* dst = (lv == t.klevel) ? d_chunks : ((cur == d_leaves) ? scratch : d_leaves);
-        rc = enqueue_level(c, cur, n, t.fanout, dst, st);
-        cur = dst; n = nn;
-    }
-    if (scratch) cudaFreeAsync(scratch, st);
-    return rc;
-}
-
-// leaves -> chunk digests for one piece resident in device memory
-int enqueue_tree_chunks(mxd_ctx* c, const Tree& t, const uint8_t* d_piece, uint64_t nbytes, uint8_t* d_chunks, cudaStream_t st) {
-    const uint64_t n0 = nbytes ? (nbytes + t.leaf - 1) / t.leaf : 1;
-    uint8_t* ws = nullptr;
-    MXD_CUDA(cudaMallocAsync(&ws, n0 * 32, st));
-    int rc = enqueue_segments(c, d_piece, nbytes, t.leaf, ws, st, /*leaf_level=*/true);
-    if (rc == MXD_OK) rc = enqueue_leaves_to_chunks(c, t, ws, n0, d_chunks, st);
-    cudaFreeAsync(ws, st);
-    return rc;
-}
-
-// levels above the chunk list, then the root message
-int enqueue_tree_finish(mxd_ctx* c, const Tree& t, const uint8_t* d_chunks, uint64_t nchunks, uint64_t size,
-                        uint8_t* d_root, cudaStream_t st) {
-    const uint8_t* cur = d_chunks;
-    uint64_t n = nchunks;
-    uint8_t* bufs[2] = {nullptr, nullptr};
-    int rc = MXD_OK, which = 0;
-    if (n > 1) {
-        const uint64_t n1 = (n + t.fanout - 1) / t.fanout;
-        for (int i = 0; i < 2 && rc == MXD_OK; ++i) {
-            cudaError_t e = cudaMallocAsync(&bufs[i], n1 * 32, st);
-            if (e != cudaSuccess) rc = fail(MXD_ERR_CUDA, std::string("cudaMallocAsync: ") + cudaGetErrorString(e));
-        }
-    }
-    while (n > 1 && rc == MXD_OK) {
-        rc = enqueue_level(c, cur, n, t.fanout, bufs[which], st);
-        cur = bufs[which]; which ^= 1;
-        n = (n + t.fanout - 1) / t.fanout;
-    }
-    if (rc == MXD_OK) {
-        cudaError_t e = mxd::launch_tree_root(size, t.leaf, (uint32_t)t.fanout, cur, d_root, st);
-        if (e != cudaSuccess) rc = fail(MXD_ERR_CUDA, std::string("launch_tree_root: ") + cudaGetErrorString(e));
-        else c->launches++;
-    }
-    for (int i = 0; i < 2; ++i) if (bufs[i]) cudaFreeAsync(bufs[i], st);
-    return rc;
-}
-
-enum class MemKind { Pageable, Pinned, Device };
 
 MemKind classify(const void* p, int* device_ordinal) {
     cudaPointerAttributes a{};
@@ -317,26 +137,17 @@ MemKind classify(const void* p, int* device_ordinal) {
     return MemKind::Pageable;
 }
 
-int dev_index_of(const mxd_ctx* c, int ordinal) {
+int dev_index_of(const Core* c, int ordinal) {
     for (size_t i = 0; i < c->devs.size(); ++i)
         if (c->devs[i]->ordinal == ordinal) return (int)i;
     return -1;
 }
 
-// ---- data sources for the streaming ring -------------------------------------------------------
-struct Source {
-    const uint8_t* mem = nullptr;  // host memory source
-    bool pinned = false;
-    int fd = -1;                   // file source
-    uint64_t base = 0;             // offset of this source's byte 0 inside the file
-    mxd_sink_fn sink = nullptr;    // optional tee: every streamed byte is also handed to this callback
-    void* sink_user = nullptr;
-    uint64_t sink_base = 0;        // logical offset of this source's byte 0 for the sink
-};
+DevState* pick_device(Core* c) { return c->devs[c->rr++ % c->devs.size()]; }
 
 // hand [off, off+n) (already staged at `data`) to the tee in <= 4 MiB pieces, in parallel on the pool
-int sink_slot(const Source& s, uint64_t off, uint64_t n, const uint8_t* data, StagePool* pool) {
-    if (!s.sink) return MXD_OK;
+int sink_pieces(const Source& s, uint64_t off, uint64_t n, const uint8_t* data, StagePool* pool) {
+    if (!s.sink || n == 0) return MXD_OK;
     constexpr uint64_t kPiece = 4ull << 20;
     const int pieces = (int)((n + kPiece - 1) / kPiece);
     std::atomic<int> bad{0};
@@ -348,10 +159,7 @@ int sink_slot(const Source& s, uint64_t off, uint64_t n, const uint8_t* data, St
     return bad.load() ? fail(MXD_ERR_IO, "sink refused data") : MXD_OK;
 }
 
-// Fill `n` bytes at logical offset `off` of the source into pinned `dst`; returns the pointer the
-// H2D copy should read from (dst, or the caller's own memory when that is already pinned).
-// Large fills are split into 4 MiB pieces across the device's StagePool.
-int source_stage(const Source& s, uint64_t off, uint64_t n, uint8_t* dst, const uint8_t** from, StagePool* pool = nullptr) {
+int source_stage(Core* c, const Source& s, uint64_t off, uint64_t n, uint8_t* dst, const uint8_t** from, StagePool* pool) {
     if (s.fd < 0 && s.pinned) { *from = s.mem + off; return MXD_OK; }
     *from = dst;
     static const uint64_t kPiece = [] { const char* e = getenv("MXD_STAGE_PIECE"); uint64_t v = e ? strtoull(e, nullptr, 10) : 0; return v >= 4096 ? v : (4ull << 20); }();
@@ -376,20 +184,176 @@ int source_stage(const Source& s, uint64_t off, uint64_t n, uint8_t* dst, const 
     const int e = err.load();
     if (e == -1) return fail(MXD_ERR_IO, "pread: file shrank while hashing");
     if (e) return fail(MXD_ERR_IO, std::string("pread: ") + strerror(e));
+    c->src_read += n;
     return MXD_OK;
 }
 
-// Stream [0, nbytes) of `src` through device `d`'s ring and hash it as uniform segments of `seg`
-// bytes into d_out (device, ceil(nbytes/seg) digests).  slot_bytes is a multiple of seg.
-// H2D copies run on the copy stream, kernels on the compute stream; a slot is refilled only
-// after the kernel that read it has finished, so copy k+1.. overlap kernel k.
-int stream_segments(mxd_ctx* c, DevState* d, const Source& src, uint64_t nbytes, uint64_t seg, uint8_t* d_out) {
-    const uint64_t per_slot = (d->slot_bytes / seg) * seg;
-    if (per_slot == 0) return fail(MXD_ERR_INVALID, "ring slot smaller than one segment; raise ring_bytes");
-    if (nbytes == 0) return enqueue_segments(c, nullptr, 0, seg, d_out, d->compute);
+namespace {
+
+// Resolved tree parameters: chunk = leaf * fanout^klevel.
+struct Tree {
+    uint64_t chunk = 8ull << 20, leaf = 16ull << 10, fanout = 8;
+    int klevel = 3;
+};
+
+bool tree_resolve(const mxd_tree_params* tp, Tree* t) {
+    if (tp) { t->chunk = tp->chunk; t->leaf = tp->leaf; t->fanout = tp->fanout; }
+    if (t->leaf < 64 || (t->leaf % 64) != 0 || t->fanout < 2 || t->chunk < t->leaf) return false;
+    if (tp && tp->reserved != 0) return false;
+    uint64_t span = t->leaf;
+    int k = 0;
+    while (span < t->chunk) {
+        if (span > t->chunk / t->fanout) return false;   // overflow / not a power
+        span *= t->fanout; ++k;
+    }
+    if (span != t->chunk || k < 1) return false;
+    t->klevel = k;
+    return true;
+}
+
+uint64_t ipow(uint64_t b, uint32_t e) { uint64_t r = 1; while (e--) r *= b; return r; }
+
+// ---- live timing of leaf launches --------------------------------------------------------------------------
+struct ProfScope {
+    Core* c; Core::ProfRec rec{}; bool on = false; cudaStream_t st;
+    ProfScope(Core* core, uint64_t nbytes, cudaStream_t stream, bool enabled = true) : c(core), st(stream) {
+        if (!enabled || !c->prof_on.load()) return;
+        { std::lock_guard<std::mutex> lk(c->prof_mu); if (c->prof.size() >= (1u << 16)) return; }   // bounded
+        cudaGetDevice(&rec.ordinal);
+        if (cudaEventCreate(&rec.a) != cudaSuccess) return;
+        if (cudaEventCreate(&rec.b) != cudaSuccess) { cudaEventDestroy(rec.a); return; }
+        rec.bytes = nbytes;
+        cudaEventRecord(rec.a, st);
+        on = true;
+    }
+    ~ProfScope() {
+        if (!on) return;
+        cudaEventRecord(rec.b, st);
+        std::lock_guard<std::mutex> lk(c->prof_mu);
+        c->prof.push_back(rec);
+    }
+};
+
+// ---- kernel enqueue helpers ------------------------------------------------------------------
+// uniform segments of device memory -> one digest each (plain SHA-256 per segment)
+int enqueue_segments(Core* c, const uint8_t* d_data, uint64_t nbytes, uint64_t seg, uint8_t* d_out, cudaStream_t st,
+                     bool leaf_level = false) {
+    ProfScope prof(c, nbytes, st, leaf_level);
+    mxd::MsgJob j{};
+    j.base = d_data; j.nbytes = nbytes; j.seg = seg;
+    j.nmsg = nbytes ? (nbytes + seg - 1) / seg : 1;
+    j.out = d_out; j.finalize = 1; j.one = 1;
+    if (j.base == nullptr) j.base = reinterpret_cast<const uint8_t*>(d_out);   // empty message: any non-null base keeps the kernel in segment mode
+    MXD_CUDA(mxd::launch_sha256(j, st));
+    c->launches++; c->bytes_hashed += nbytes;
+    return MXD_OK;
+}
+
+// digests of one tree level -> the next: groups of `fanout` digests
+int enqueue_level(Core* c, const uint8_t* d_in, uint64_t n, uint64_t fanout, uint8_t* d_out, cudaStream_t st) {
+    return enqueue_segments(c, d_in, n * 32, 32 * fanout, d_out, st);
+}
+
+// How many tree levels the leaf kernel computes itself for this tree when a piece is at least `avail` bytes long
+// (0 = legacy path: plain leaf digests, every level its own launch; MXD_TUNE_LEAF=legacy forces that).
+uint32_t fused_levels(const Tree& t, uint64_t avail) {
+    static const bool legacy = [] { const char* e = getenv("MXD_TUNE_LEAF"); return e && !strcmp(e, "legacy"); }();
+    if (legacy) return 0;
+    uint32_t f = mxd::leaf_fusable_levels((uint32_t)t.fanout, (uint32_t)t.klevel);
+    while (f > 0 && t.leaf * ipow(t.fanout, f) > avail) --f;
+    return f;
+}
+
+// blob bytes in device memory -> digests of tree level `fused` (one launch, leaves never touch DRAM when fused > 0)
+int enqueue_leaves(Core* c, const Tree& t, uint32_t fused, const uint8_t* d_piece, uint64_t nbytes, uint8_t* d_out, cudaStream_t st) {
+    const uint64_t n0 = nbytes ? (nbytes + t.leaf - 1) / t.leaf : 1;
+    static const bool legacy = [] { const char* e = getenv("MXD_TUNE_LEAF"); return e && !strcmp(e, "legacy"); }();
+    if (legacy) return enqueue_segments(c, d_piece, nbytes, t.leaf, d_out, st, /*leaf_level=*/true);
+    ProfScope prof(c, nbytes, st);
+    uint32_t* sched = nullptr;
+    MXD_CUDA(cudaMallocAsync(&sched, mxd::leaf_sched_bytes(n0), st));
+    mxd::LeafJob j{};
+    j.base = d_piece ? d_piece : reinterpret_cast<const uint8_t*>(d_out);
+    j.nbytes = nbytes; j.leaf = t.leaf; j.n0 = n0; j.fanout = (uint32_t)t.fanout; j.fused = fused;
+    j.out = d_out; j.sched = sched; j.one = 1;
+    cudaError_t e = mxd::launch_tree_leaves(j, st);
+    cudaFreeAsync(sched, st);
+    if (e != cudaSuccess) return fail(MXD_ERR_CUDA, std::string("launch_tree_leaves: ") + cudaGetErrorString(e));
+    c->launches++; c->bytes_hashed += nbytes;
+    return MXD_OK;
+}
+
+// digests of level `from` (n of them in d_in, clobbered as scratch) -> chunk digests (level k)
+int enqueue_levels_to_chunks(Core* c, const Tree& t, uint32_t from, uint8_t* d_in, uint64_t n, uint8_t* d_chunks, cudaStream_t st) {
+    if ((int)from >= t.klevel) return MXD_OK;     // the caller wrote level k straight into d_chunks
+    const uint64_t n1 = (n + t.fanout - 1) / t.fanout;
+    uint8_t* scratch = nullptr;
+    if (t.klevel - (int)from > 1) MXD_CUDA(cudaMallocAsync(&scratch, n1 * 32, st));
+    uint8_t* cur = d_in;
+    int rc = MXD_OK;
+    for (int lv = (int)from + 1; lv <= t.klevel && rc == MXD_OK; ++lv) {
+        const uint64_t nn = (n + t.fanout - 1) / t.fanout;
+        uint8_t* dst = (lv == t.klevel) ? d_chunks : ((cur == d_in) ? scratch : d_in);
+        rc = enqueue_level(c, cur, n, t.fanout, dst, st);
+        cur = dst; n = nn;
+    }
+    if (scratch) cudaFreeAsync(scratch, st);
+    return rc;
+}
+
+// leaves -> chunk digests for one piece resident in device memory
+int enqueue_tree_chunks(Core* c, const Tree& t, const uint8_t* d_piece, uint64_t nbytes, uint8_t* d_chunks, cudaStream_t st) {
+    const uint64_t n0 = nbytes ? (nbytes + t.leaf - 1) / t.leaf : 1;
+    const uint32_t fused = fused_levels(t, ~0ull);
+    if ((int)fused == t.klevel) return enqueue_leaves(c, t, fused, d_piece, nbytes, d_chunks, st);
+    const uint64_t span = ipow(t.fanout, fused);
+    const uint64_t nf = (n0 + span - 1) / span;
+    uint8_t* ws = nullptr;
+    MXD_CUDA(cudaMallocAsync(&ws, nf * 32, st));
+    int rc = enqueue_leaves(c, t, fused, d_piece, nbytes, ws, st);
+    if (rc == MXD_OK) rc = enqueue_levels_to_chunks(c, t, fused, ws, nf, d_chunks, st);
+    cudaFreeAsync(ws, st);
+    return rc;
+}
+
+// levels above the chunk list, then the root message
+int enqueue_tree_finish(Core* c, const Tree& t, const uint8_t* d_chunks, uint64_t nchunks, uint64_t size,
+                        uint8_t* d_root, cudaStream_t st) {
+    uint8_t* scratch = nullptr;
+    MXD_CUDA(cudaMallocAsync(&scratch, mxd::tree_top_scratch_bytes(nchunks, (uint32_t)t.fanout), st));
+    cudaError_t e = mxd::launch_tree_top(d_chunks, nchunks, (uint32_t)t.fanout, size, t.leaf, scratch, d_root, st);
+    cudaFreeAsync(scratch, st);
+    if (e != cudaSuccess) return fail(MXD_ERR_CUDA, std::string("launch_tree_top: ") + cudaGetErrorString(e));
+    c->launches++;
+    return MXD_OK;
+}
+
+// ---- slot timeline ---------------------------------------------------------------------------------------------
+struct TraceSlot {
+    Core* c; Core::TraceRec rec{}; bool on = false;
+    TraceSlot(Core* core, int ordinal, int slot, uint64_t bytes, double fill_ms) : c(core) {
+        if (!c->trace_on.load()) return;
+        { std::lock_guard<std::mutex> lk(c->trace_mu); if (c->trace.size() >= (1u << 15)) return; }
+        rec.ordinal = ordinal; rec.slot = slot; rec.bytes = bytes; rec.fill_ms = fill_ms;
+        if (cudaEventCreate(&rec.c0) != cudaSuccess || cudaEventCreate(&rec.c1) != cudaSuccess ||
+            cudaEventCreate(&rec.k0) != cudaSuccess || cudaEventCreate(&rec.k1) != cudaSuccess) return;
+        on = true;
+    }
+    void commit() { if (on) { std::lock_guard<std::mutex> lk(c->trace_mu); c->trace.push_back(rec); } }
+};
+
+// Stream [0, nbytes) of `src` through device `d`'s ring and hash it as tree leaves of t.leaf bytes (with `fused`
+// levels computed in the same kernel) into d_out.  H2D copies run on the copy stream, kernels on the compute
+// stream; a slot is refilled only after the kernel that read it has finished, so copy k+1.. overlap kernel k.
+int stream_leaves(Core* c, const CancelScope& cs, DevState* d, const Tree& t, uint32_t fused, const Source& src, uint64_t nbytes,
+                  uint8_t* d_out) {
+    const uint64_t unit = t.leaf * ipow(t.fanout, fused);       // bytes under one output digest
+    const uint64_t per_slot = (d->slot_bytes / unit) * unit;
+    if (per_slot == 0) return fail(MXD_ERR_INVALID, "ring slot smaller than one leaf; raise ring_bytes");
+    if (nbytes == 0) return enqueue_leaves(c, t, fused, nullptr, 0, d_out, d->compute);
     uint64_t off = 0;
     for (uint64_t i = 0; off < nbytes; ++i) {
-        if (c->canceled.load()) return fail(MXD_ERR_CANCELED, "canceled");
+        if (cs.canceled()) return fail(MXD_ERR_CANCELED, "canceled");
         const int s = (int)(i % kSlots);
         const uint64_t n = (nbytes - off < per_slot) ? nbytes - off : per_slot;
         if (i >= (uint64_t)kSlots) MXD_CUDA(cudaEventSynchronize(d->ev_done[s]));
@@ -397,15 +361,22 @@ int stream_segments(mxd_ctx* c, DevState* d, const Source& src, uint64_t nbytes,
         uint8_t* d_slot = d->d_ring + (uint64_t)s * d->slot_bytes;
         const uint8_t* from = nullptr;
         int rc;
-        { PhaseTimer pt("  fill slot"); rc = source_stage(src, off, n, h_slot, &from, d->pool); }
+        const double f0 = c->trace_on.load() ? now_ms() : 0;
+        { PhaseTimer pt("  fill slot"); rc = source_stage(c, src, off, n, h_slot, &from, d->pool); }
         if (rc != MXD_OK) return rc;
+        TraceSlot tr(c, d->ordinal, s, n, c->trace_on.load() ? now_ms() - f0 : 0);
+        if (tr.on) cudaEventRecord(tr.rec.c0, d->copy);
         MXD_CUDA(cudaMemcpyAsync(d_slot, from, n, cudaMemcpyHostToDevice, d->copy));
+        if (tr.on) cudaEventRecord(tr.rec.c1, d->copy);
         MXD_CUDA(cudaEventRecord(d->ev_copied[s], d->copy));
         MXD_CUDA(cudaStreamWaitEvent(d->compute, d->ev_copied[s], 0));
-        rc = enqueue_segments(c, d_slot, n, seg, d_out + (off / seg) * 32, d->compute, /*leaf_level=*/true);
+        if (tr.on) cudaEventRecord(tr.rec.k0, d->compute);
+        rc = enqueue_leaves(c, t, fused, d_slot, n, d_out + (off / unit) * 32, d->compute);
         if (rc != MXD_OK) return rc;
+        if (tr.on) cudaEventRecord(tr.rec.k1, d->compute);
+        tr.commit();
         MXD_CUDA(cudaEventRecord(d->ev_done[s], d->compute));
-        rc = sink_slot(src, off, n, from, d->pool);     // the tee runs while the copy engine and the SMs work on this slot
+        rc = sink_pieces(src, off, n, from, d->pool);     // the tee runs while the copy engine and the SMs work on this slot
         if (rc != MXD_OK) return rc;
         c->h2d += n;
         off += n;
@@ -414,25 +385,29 @@ int stream_segments(mxd_ctx* c, DevState* d, const Source& src, uint64_t nbytes,
 }
 
 // chunk digests of a host/file piece on one device; result left in device memory d_chunks
-int stream_tree_chunks(mxd_ctx* c, DevState* d, const Tree& t, const Source& src, uint64_t nbytes, uint8_t* d_chunks) {
+int stream_tree_chunks(Core* c, const CancelScope& cs, DevState* d, const Tree& t, const Source& src, uint64_t nbytes, uint8_t* d_chunks) {
     const uint64_t n0 = nbytes ? (nbytes + t.leaf - 1) / t.leaf : 1;
-    uint8_t* d_leaves = nullptr;
-    { PhaseTimer pt("alloc leaf digests"); MXD_CUDA(cudaMallocAsync(&d_leaves, n0 * 32, d->compute)); }
+    const uint32_t fused = fused_levels(t, d->slot_bytes);
+    const uint64_t span = ipow(t.fanout, fused);
+    const uint64_t nf = (n0 + span - 1) / span;
+    const bool direct = (int)fused == t.klevel;
+    uint8_t* d_lvl = d_chunks;
+    if (!direct) { PhaseTimer pt("alloc level digests"); MXD_CUDA(cudaMallocAsync(&d_lvl, nf * 32, d->compute)); }
     int rc;
-    { PhaseTimer pt("stream_segments (enqueue)"); rc = stream_segments(c, d, src, nbytes, t.leaf, d_leaves); }
-    if (rc == MXD_OK) rc = enqueue_leaves_to_chunks(c, t, d_leaves, n0, d_chunks, d->compute);
+    { PhaseTimer pt("stream_leaves (enqueue)"); rc = stream_leaves(c, cs, d, t, fused, src, nbytes, d_lvl); }
+    if (rc == MXD_OK && !direct) rc = enqueue_levels_to_chunks(c, t, fused, d_lvl, nf, d_chunks, d->compute);
     if (rc != MXD_OK) cudaStreamSynchronize(d->copy);   // nothing may still be reading the caller's (pinned) memory
     cudaError_t e;
     { PhaseTimer pt("sync compute"); e = cudaStreamSynchronize(d->compute); }
     if (rc == MXD_OK && e != cudaSuccess) rc = fail(MXD_ERR_CUDA, std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e));
-    cudaFreeAsync(d_leaves, d->compute);
+    if (!direct) cudaFreeAsync(d_lvl, d->compute);
     return rc;
 }
 
 // Chunk digests of a host/file blob using every device of the context: device g takes the
 // contiguous chunk range [g*n/G, (g+1)*n/G) (sequential reads per device, no data-path
 // collective).  Results land in host memory `out` (nchunks*32).
-int host_tree_chunks_all(mxd_ctx* c, const Tree& t, const Source& src, uint64_t nbytes, uint8_t* out) {
+int host_tree_chunks_all(Core* c, const CancelScope& cs, const Tree& t, const Source& src, uint64_t nbytes, uint8_t* out) {
     const uint64_t chunk = t.chunk;
     const uint64_t nchunks = nbytes ? (nbytes + chunk - 1) / chunk : 1;
     const int G = (int)std::min<uint64_t>(c->devs.size(), nchunks);
@@ -450,24 +425,24 @@ int host_tree_chunks_all(mxd_ctx* c, const Tree& t, const Source& src, uint64_t 
         uint8_t* d_chunks = nullptr;
         cudaError_t e = cudaMallocAsync(&d_chunks, (c1 - c0) * 32, d->compute);
         if (e != cudaSuccess) { rcs[g] = MXD_ERR_CUDA; errs[g] = cudaGetErrorString(e); return; }
-        int rc = stream_tree_chunks(c, d, t, piece, b1 - b0, d_chunks);
+        int rc = stream_tree_chunks(c, cs, d, t, piece, b1 - b0, d_chunks);
         if (rc == MXD_OK) {
             PhaseTimer pt("chunk digests D2H");
             e = cudaMemcpyAsync(out + c0 * 32, d_chunks, (c1 - c0) * 32, cudaMemcpyDeviceToHost, d->compute);
             if (e == cudaSuccess) e = cudaStreamSynchronize(d->compute);
-            if (e != cudaSuccess) { rc = MXD_ERR_CUDA; g_last_error = cudaGetErrorString(e); }
+            if (e != cudaSuccess) { rc = MXD_ERR_CUDA; fail(rc, cudaGetErrorString(e)); }
             c->d2h += (c1 - c0) * 32;
         }
         cudaFreeAsync(d_chunks, d->compute);
         rcs[g] = rc;
-        if (rc != MXD_OK) errs[g] = g_last_error;
+        if (rc != MXD_OK) errs[g] = last_error();
     };
     if (G == 1) {
         work(0);
     } else {
         std::vector<std::thread> th;
         for (int g = 0; g < G; ++g) th.emplace_back(work, g);
-        for (auto& t : th) t.join();
+        for (auto& t2 : th) t2.join();
     }
     for (int g = 0; g < G; ++g)
         if (rcs[g] != MXD_OK) return fail(rcs[g], errs[g]);
@@ -475,7 +450,7 @@ int host_tree_chunks_all(mxd_ctx* c, const Tree& t, const Source& src, uint64_t 
 }
 
 // upper levels + root from a host-resident chunk list (tiny: 32 B per chunk)
-int host_tree_finish(mxd_ctx* c, DevState* d, const Tree& t, const uint8_t* chunks, uint64_t nchunks, uint64_t size,
+int host_tree_finish(Core* c, DevState* d, const Tree& t, const uint8_t* chunks, uint64_t nchunks, uint64_t size,
                      uint8_t root[32]) {
     PhaseTimer pt("tree finish (levels + root)");
     std::lock_guard<std::mutex> lk(d->mu);
@@ -498,179 +473,12 @@ int host_tree_finish(mxd_ctx* c, DevState* d, const Tree& t, const uint8_t* chun
     return rc;
 }
 
-DevState* pick_device(mxd_ctx* c) { return c->devs[c->rr++ % c->devs.size()]; }
-
-// ---- lock-step hashing of n whole messages from host sources (files or host spans) -------------
-// Round k moves bytes [k*S, (k+1)*S) of every still-running message into one ring slot
-// (message i at slot offset i*S) and advances all chains together; each lane carries its chain
-// state in device memory between rounds.  This is the reference's one-digest-per-file result
-// (push.go:149-161) for many files at once.
-struct LockstepInput {
-    std::vector<Source> src;
-    std::vector<uint64_t> len;
-};
-
-int lockstep_digest(mxd_ctx* c, DevState* d, const LockstepInput& in, uint8_t* out) {
-    const uint64_t n = in.src.size();
-    if (n == 0) return MXD_OK;
-    std::lock_guard<std::mutex> lk(d->mu);
-    DeviceGuard guard(d->ordinal);
-    if ((d->slot_bytes / n) < 64) return fail(MXD_ERR_INVALID, "too many messages for the ring slot; raise ring_bytes or split the batch");
-    // Per round every still-running message advances by S bytes, S = slot / (running messages) rounded down to
-    // 64 and capped at 8 MiB; finished messages give their share of the slot to the rest, and only the
-    // occupied part of the slot is copied.
-    std::vector<uint64_t> done(n, 0);
-    std::vector<uint8_t> finished(n, 0);
-    uint64_t running = n;
-
-    // per-round descriptors live in pinned memory, double-buffered per slot
-    const uint64_t desc_bytes = (n * (sizeof(mxd::DevSpan) + sizeof(uint64_t) + 1) + 255) & ~255ull;
-    // Scratch: pinned descriptors are kept in the device state (cudaMallocHost costs ~0.5 ms, too much for small
-    // calls); device buffers come from the stream-ordered pool, which mxd_open told to keep freed memory cached.
-    if (d->h_desc_bytes < desc_bytes * kSlots) {
-        if (d->h_desc) cudaFreeHost(d->h_desc);
-        d->h_desc = nullptr; d->h_desc_bytes = 0;
-        const uint64_t want = std::max<uint64_t>(desc_bytes * kSlots, 64 << 10);
-        MXD_CUDA(cudaHostAlloc(&d->h_desc, want, cudaHostAllocPortable));
-        d->h_desc_bytes = want;
-    }
-    uint8_t *h_desc = d->h_desc, *d_desc = nullptr, *d_out = nullptr;
-    uint32_t* d_state = nullptr;
-    int rc = MXD_OK;
-    cudaError_t e;
-    if ((e = cudaMallocAsync(&d_desc, desc_bytes * kSlots, d->compute)) != cudaSuccess ||
-        (e = cudaMallocAsync(&d_out, n * 32, d->compute)) != cudaSuccess ||
-        (e = cudaMallocAsync(&d_state, n * 32, d->compute)) != cudaSuccess) {
-        rc = fail(MXD_ERR_CUDA, std::string("cudaMallocAsync: ") + cudaGetErrorString(e));
-    }
-    if (rc == MXD_OK) {  // every chain starts from the FIPS 180-4 initial hash value
-        std::vector<uint32_t> iv(n * 8);
-        for (uint64_t i = 0; i < n; ++i) memcpy(&iv[8 * i], kIVHost, 32);
-        e = cudaMemcpyAsync(d_state, iv.data(), n * 32, cudaMemcpyHostToDevice, d->compute);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(d->compute);   // iv is a stack/heap temporary; also orders the pool allocations before the copy stream uses them
-        if (e != cudaSuccess) rc = fail(MXD_ERR_CUDA, cudaGetErrorString(e));
-    }
-    for (uint64_t k = 0; running > 0 && rc == MXD_OK; ++k) {
-        if (c->canceled.load()) { rc = fail(MXD_ERR_CANCELED, "canceled"); break; }
-        const int s = (int)(k % kSlots);
-        if (k >= (uint64_t)kSlots) {
-            e = cudaEventSynchronize(d->ev_done[s]);
-            if (e != cudaSuccess) { rc = fail(MXD_ERR_CUDA, cudaGetErrorString(e)); break; }
-        }
-        uint8_t* h_slot = d->h_ring + (uint64_t)s * d->slot_bytes;
-        uint8_t* d_slot = d->d_ring + (uint64_t)s * d->slot_bytes;
-        uint8_t* hd = h_desc + desc_bytes * s;
-        auto* spans = reinterpret_cast<mxd::DevSpan*>(hd);
-        auto* prefix = reinterpret_cast<uint64_t*>(hd + n * sizeof(mxd::DevSpan));
-        uint8_t* ctl = hd + n * (sizeof(mxd::DevSpan) + sizeof(uint64_t));
-        const uint64_t S = std::min<uint64_t>(8ull << 20, (d->slot_bytes / running) & ~63ull);
-        uint64_t moved = 0, pos = 0;
-        struct Fill { uint64_t i, done, take, pos; };
-        std::vector<Fill> fills;
-        for (uint64_t i = 0; i < n; ++i) {
-            if (finished[i]) { spans[i] = {d_slot, 0}; prefix[i] = in.len[i]; ctl[i] = 2; continue; }
-            const uint64_t take = std::min(in.len[i] - done[i], S);
-            const bool last = done[i] + take == in.len[i];     // finalised in the round that reaches its end
-            spans[i] = {d_slot + pos * S, take};
-            prefix[i] = done[i];
-            ctl[i] = last ? 1 : 0;
-            if (take) { fills.push_back({i, done[i], take, pos}); ++pos; }   // empty messages occupy no slot space
-            moved += take; done[i] += take;
-            if (last) finished[i] = 1;
-        }
-        const uint64_t occupied = pos * S;
-        running = 0;
-        for (uint64_t i = 0; i < n; ++i) running += finished[i] ? 0 : 1;
-        // gather this round's bytes of every running message into the slot, files read in parallel
-        std::vector<int> frc(fills.size(), MXD_OK);
-        std::vector<std::string> ferr(fills.size());
-        d->pool->parallel_for((int)fills.size(), [&](int f) {
-            Source one = in.src[fills[f].i];
-            one.pinned = false;   // always copy into the slot so the whole round is one H2D transfer
-            const uint8_t* from = nullptr;
-            frc[f] = source_stage(one, fills[f].done, fills[f].take, h_slot + fills[f].pos * S, &from);
-            if (frc[f] != MXD_OK) ferr[f] = g_last_error;
-        });
-        for (size_t f = 0; f < fills.size(); ++f) if (frc[f] != MXD_OK) { rc = fail(frc[f], ferr[f]); break; }
-        if (rc != MXD_OK) break;
-        const uint64_t span_bytes = occupied;
-        e = span_bytes ? cudaMemcpyAsync(d_slot, h_slot, span_bytes, cudaMemcpyHostToDevice, d->copy) : cudaSuccess;
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_desc + desc_bytes * s, hd, desc_bytes, cudaMemcpyHostToDevice, d->copy);
-        if (e == cudaSuccess) e = cudaEventRecord(d->ev_copied[s], d->copy);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(d->compute, d->ev_copied[s], 0);
-        if (e != cudaSuccess) { rc = fail(MXD_ERR_CUDA, cudaGetErrorString(e)); break; }
-        mxd::MsgJob j{};
-        uint8_t* dd = d_desc + desc_bytes * s;
-        j.spans = dd; j.nmsg = n; j.out = d_out; j.state = d_state;
-        j.prefix = reinterpret_cast<const uint64_t*>(dd + n * sizeof(mxd::DevSpan));
-        j.ctl = dd + n * (sizeof(mxd::DevSpan) + sizeof(uint64_t));
-        j.finalize = 0; j.one = 1;
-        e = mxd::launch_sha256(j, d->compute);
-        if (e == cudaSuccess) e = cudaEventRecord(d->ev_done[s], d->compute);
-        if (e != cudaSuccess) { rc = fail(MXD_ERR_CUDA, cudaGetErrorString(e)); break; }
-        c->launches++; c->bytes_hashed += moved; c->h2d += span_bytes + desc_bytes;
-    }
-    if (rc == MXD_OK) {
-        e = cudaMemcpyAsync(out, d_out, n * 32, cudaMemcpyDeviceToHost, d->compute);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(d->compute);
-        if (e != cudaSuccess) rc = fail(MXD_ERR_CUDA, cudaGetErrorString(e));
-        c->d2h += n * 32;
-    } else {
-        cudaStreamSynchronize(d->compute); cudaStreamSynchronize(d->copy);
-    }
-    if (d_state) cudaFreeAsync(d_state, d->compute);
-    if (d_out) cudaFreeAsync(d_out, d->compute);
-    if (d_desc) cudaFreeAsync(d_desc, d->compute);
-    return rc;
-}
-
-// Spread a batch of whole messages over every device of the context (largest first onto the least
-// loaded device), one lock-step batch per device running concurrently; results keep the caller's order.
-int lockstep_digest_all(mxd_ctx* c, const LockstepInput& in, uint8_t* out) {
-    const uint64_t n = in.src.size();
-    const size_t G = std::min<uint64_t>(c->devs.size(), std::max<uint64_t>(n, 1));
-    if (G <= 1) return lockstep_digest(c, pick_device(c), in, out);
-    std::vector<uint64_t> order(n);
-    for (uint64_t i = 0; i < n; ++i) order[i] = i;
-    std::sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) { return in.len[a] > in.len[b]; });
-    std::vector<std::vector<uint64_t>> group(G);
-    std::vector<uint64_t> load(G, 0);
-    for (uint64_t idx : order) {
-        size_t g = (size_t)(std::min_element(load.begin(), load.end()) - load.begin());
-        group[g].push_back(idx); load[g] += in.len[idx] + 1;
-    }
-    std::vector<int> rcs(G, MXD_OK);
-    std::vector<std::string> errs(G);
-    std::vector<std::thread> th;
-    for (size_t g = 0; g < G; ++g) th.emplace_back([&, g] {
-        LockstepInput part;
-        for (uint64_t idx : group[g]) { part.src.push_back(in.src[idx]); part.len.push_back(in.len[idx]); }
-        std::vector<uint8_t> o(32 * part.src.size());
-        rcs[g] = lockstep_digest(c, c->devs[g], part, o.data());
-        if (rcs[g] != MXD_OK) { errs[g] = g_last_error; return; }
-        for (size_t k = 0; k < group[g].size(); ++k) memcpy(out + 32 * group[g][k], &o[32 * k], 32);
-    });
-    for (auto& t : th) t.join();
-    for (size_t g = 0; g < G; ++g) if (rcs[g] != MXD_OK) return fail(rcs[g], errs[g]);
-    return MXD_OK;
-}
-
-int open_files(const char* const* paths, uint64_t n, LockstepInput* in, std::vector<int>* fds) {
-    in->src.resize(n); in->len.resize(n);
-    for (uint64_t i = 0; i < n; ++i) {
-        int fd = open(paths[i], O_RDONLY | O_CLOEXEC);
-        if (fd < 0) { int e = errno; for (int f : *fds) close(f); fds->clear(); errno = e;
-                      return fail(MXD_ERR_IO, std::string("open ") + paths[i] + ": " + strerror(e)); }
-        fds->push_back(fd);
-        struct stat st;
-        if (fstat(fd, &st) != 0) { int e = errno; for (int f : *fds) close(f); fds->clear(); errno = e;
-                                   return fail(MXD_ERR_IO, std::string("fstat ") + paths[i] + ": " + strerror(e)); }
-        in->src[i].fd = fd; in->len[i] = (uint64_t)st.st_size;
-    }
-    return MXD_OK;
-}
+bool handle_ok(const mxd_ctx* h) { return h != nullptr && h->core != nullptr; }
 
 }  // namespace
+}  // namespace mxdi
+
+using namespace mxdi;
 
 // =================================================================================================
 extern "C" {
@@ -691,17 +499,18 @@ const char* mxd_strerror(int status) {
     }
 }
 
-const char* mxd_last_error(void) { return g_last_error.c_str(); }
+const char* mxd_last_error(void) { return last_error().c_str(); }
 
-int mxd_prof_enable(mxd_ctx* c, int on) {
-    if (!c) return fail(MXD_ERR_INVALID, "prof_enable: null");
-    c->prof_on.store(on ? 1 : 0);
+int mxd_prof_enable(mxd_ctx* h, int on) {
+    if (!handle_ok(h)) return fail(MXD_ERR_INVALID, "prof_enable: null");
+    h->core->prof_on.store(on ? 1 : 0);
     return MXD_OK;
 }
 
-int mxd_prof_read(mxd_ctx* c, double* kernel_ms, uint64_t* launches, uint64_t* bytes) {
-    if (!c) return fail(MXD_ERR_INVALID, "prof_read: null");
-    std::vector<mxd_ctx::ProfRec> recs;
+int mxd_prof_read(mxd_ctx* h, double* kernel_ms, uint64_t* launches, uint64_t* bytes) {
+    if (!handle_ok(h)) return fail(MXD_ERR_INVALID, "prof_read: null");
+    Core* c = h->core;
+    std::vector<Core::ProfRec> recs;
     { std::lock_guard<std::mutex> lk(c->prof_mu); recs.swap(c->prof); }
     double ms = 0; uint64_t nb = 0;
     int rc = MXD_OK;
@@ -717,6 +526,40 @@ int mxd_prof_read(mxd_ctx* c, double* kernel_ms, uint64_t* launches, uint64_t* b
     if (kernel_ms) *kernel_ms = ms;
     if (launches) *launches = recs.size();
     if (bytes) *bytes = nb;
+    return rc;
+}
+
+int mxd_trace_enable(mxd_ctx* h, int on) {
+    if (!handle_ok(h)) return fail(MXD_ERR_INVALID, "trace_enable: null");
+    h->core->trace_on.store(on ? 1 : 0);
+    return MXD_OK;
+}
+
+int mxd_trace_dump(mxd_ctx* h, const char* path) {
+    if (!handle_ok(h) || !path) return fail(MXD_ERR_INVALID, "trace_dump: bad arguments");
+    Core* c = h->core;
+    std::vector<Core::TraceRec> recs;
+    { std::lock_guard<std::mutex> lk(c->trace_mu); recs.swap(c->trace); }
+    FILE* f = fopen(path, "w");
+    if (!f) return fail(MXD_ERR_IO, std::string("open ") + path + ": " + strerror(errno));
+    fprintf(f, "device,slot,bytes,host_fill_ms,h2d_start_ms,h2d_end_ms,kernel_start_ms,kernel_end_ms\n");
+    int rc = MXD_OK;
+    std::vector<cudaEvent_t> origin(64, nullptr);      // per device: the first record's copy start
+    for (auto& r : recs) {
+        DeviceGuard guard(r.ordinal);
+        if (r.ordinal >= 0 && r.ordinal < 64 && !origin[r.ordinal]) origin[r.ordinal] = r.c0;
+        cudaEvent_t o = (r.ordinal >= 0 && r.ordinal < 64) ? origin[r.ordinal] : r.c0;
+        float c0 = 0, c1 = 0, k0 = 0, k1 = 0;
+        cudaError_t e = cudaEventSynchronize(r.k1);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&c0, o, r.c0);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&c1, o, r.c1);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&k0, o, r.k0);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&k1, o, r.k1);
+        if (e != cudaSuccess) rc = fail(MXD_ERR_CUDA, std::string("trace_dump: ") + cudaGetErrorString(e));
+        fprintf(f, "%d,%d,%llu,%.3f,%.3f,%.3f,%.3f,%.3f\n", r.ordinal, r.slot, (unsigned long long)r.bytes, r.fill_ms, c0, c1, k0, k1);
+    }
+    for (auto& r : recs) { DeviceGuard guard(r.ordinal); cudaEventDestroy(r.c0); cudaEventDestroy(r.c1); cudaEventDestroy(r.k0); cudaEventDestroy(r.k1); }
+    fclose(f);
     return rc;
 }
 
@@ -740,9 +583,16 @@ int mxd_open(mxd_ctx** out, const int* devices, int ndev, uint64_t ring_bytes) {
     uint64_t slot = (ring_bytes / kSlots) & ~((1ull << 20) - 1);
     if (slot < (1ull << 20)) slot = 1ull << 20;
 
-    auto* c = new mxd_ctx();
+    auto* c = new Core();
+    auto* h = new mxd_ctx();
+    h->core = c;
+    // the digest service keeps at most this many files open at once (the reference holds 3: push.go:27)
+    struct rlimit rl;
+    if (getrlimit(RLIMIT_NOFILE, &rl) == 0 && rl.rlim_cur != RLIM_INFINITY)
+        c->fd_cap = (int)std::max<long>(8, std::min<long>(4096, (long)rl.rlim_cur / 2 - 32));
+    else c->fd_cap = 4096;
+    if (const char* env = getenv("MXD_MAX_OPEN_FILES")) { int v = atoi(env); if (v > 0) c->fd_cap = v; }
     int prev = -1; cudaGetDevice(&prev);
-    int rc = MXD_OK;
     // slot-filler threads per device: MXD_STAGE_THREADS, default min(16, hw threads / devices), at least 1
     // (page-cache pread runs at 2-4 GB/s per thread; 16 threads gave 43.5 GB/s from a tmpfs file, 32 only 30.5)
     int stage_threads = 0;
@@ -776,19 +626,22 @@ int mxd_open(mxd_ctx** out, const int* devices, int ndev, uint64_t ring_bytes) {
     }
     if (prev >= 0) cudaSetDevice(prev);
     if (e != cudaSuccess) {
-        rc = fail(MXD_ERR_CUDA, std::string("mxd_open: ") + cudaGetErrorString(e));
-        mxd_close(c);
+        int rc = fail(MXD_ERR_CUDA, std::string("mxd_open: ") + cudaGetErrorString(e));
+        mxd_close(h);
         return rc;
     }
-    *out = c;
+    *out = h;
     return MXD_OK;
 }
 
-void mxd_close(mxd_ctx* c) {
-    if (!c) return;
+void mxd_close(mxd_ctx* h) {
+    if (!h) return;
+    if (h->parent) { mxd_op_end(h); return; }     // closing an operation handle ends the operation only
+    Core* c = h->core;
     int prev = -1; cudaGetDevice(&prev);
     for (DevState* d : c->devs) {
         if (d->ordinal >= 0) cudaSetDevice(d->ordinal);
+        svc_destroy(d);
         if (d->compute) { cudaStreamSynchronize(d->compute); cudaStreamDestroy(d->compute); }
         if (d->copy) { cudaStreamSynchronize(d->copy); cudaStreamDestroy(d->copy); }
         for (int s = 0; s < kSlots; ++s) {
@@ -797,23 +650,48 @@ void mxd_close(mxd_ctx* c) {
         }
         if (d->h_ring) cudaFreeHost(d->h_ring);
         if (d->d_ring) cudaFree(d->d_ring);
-        if (d->h_desc) cudaFreeHost(d->h_desc);
         delete d->pool;
         delete d;
     }
     if (prev >= 0) cudaSetDevice(prev);
     delete c;
+    delete h;
 }
 
-int mxd_device_count(const mxd_ctx* c) { return c ? (int)c->devs.size() : 0; }
-void mxd_cancel(mxd_ctx* c) { if (c) c->canceled.store(1); }
-void mxd_reset_cancel(mxd_ctx* c) { if (c) c->canceled.store(0); }
+int mxd_op_begin(mxd_ctx* parent, mxd_ctx** op) {
+    if (!handle_ok(parent) || !op) return fail(MXD_ERR_INVALID, "op_begin: bad arguments");
+    auto* h = new mxd_ctx();
+    h->core = parent->core;
+    h->parent = parent->parent ? parent->parent : parent;
+    h->core->live_ops++;
+    *op = h;
+    return MXD_OK;
+}
 
-int mxd_get_stats(const mxd_ctx* c, mxd_stats* out) {
-    if (!c || !out) return fail(MXD_ERR_INVALID, "mxd_get_stats: null");
+void mxd_op_end(mxd_ctx* op) {
+    if (!op || !op->parent) return;
+    op->core->live_ops--;
+    delete op;
+}
+
+int mxd_device_count(const mxd_ctx* h) { return handle_ok(h) ? (int)h->core->devs.size() : 0; }
+
+void mxd_cancel(mxd_ctx* h) {
+    if (!handle_ok(h)) return;
+    if (h->parent) h->canceled.store(1);          // this operation only, and for good
+    else h->core->cancel_gen++;                   // every call in flight on the context right now; later calls are unaffected
+}
+void mxd_reset_cancel(mxd_ctx* h) { if (handle_ok(h)) h->canceled.store(0); }
+int mxd_is_canceled(const mxd_ctx* h) { return handle_ok(h) && h->canceled.load() ? 1 : 0; }
+
+int mxd_get_stats(const mxd_ctx* h, mxd_stats* out) {
+    if (!handle_ok(h) || !out) return fail(MXD_ERR_INVALID, "mxd_get_stats: null");
+    const Core* c = h->core;
     memset(out, 0, sizeof *out);
     out->kernel_launches = c->launches.load(); out->bytes_hashed = c->bytes_hashed.load();
     out->h2d_bytes = c->h2d.load(); out->d2h_bytes = c->d2h.load();
+    out->src_bytes_read = c->src_read.load();
+    out->open_files = (uint64_t)std::max(0, c->open_fds.load());
     return MXD_OK;
 }
 
@@ -836,6 +714,20 @@ int64_t mxd_server_part_count(int64_t size, int force_multipart) {
     int64_t count = size / kThreshold;
     if (count == 0) return kDefaultParts;
     return (size % kThreshold) ? count + 1 : count;
+}
+
+// ---- routing advice ------------------------------------------------------------------------------------------
+// A whole-file SHA-256 is one serial chain: ~0.09 GB/s on one GPU lane against ~1.4 GB/s on one SHA-NI core, and the
+// reference hashes 3 files at a time (push.go:27).  The GPU wins only through width.  Model (measured rates, see
+// INTEGRATION.md section 3): GPU time = max(longest blob / chain rate, total / PCIe rate) + launch overhead;
+// CPU time = max(longest blob / core rate, total / (3 cores)).
+int mxd_batch_pays_off(uint64_t n_blobs, uint64_t total_bytes, uint64_t max_blob_bytes) {
+    if (n_blobs == 0) return 0;
+    if (max_blob_bytes == 0 || max_blob_bytes > total_bytes) max_blob_bytes = (total_bytes + n_blobs - 1) / n_blobs;
+    const double chain = 0.085e9, pcie = 45e9, core = 1.4e9, cpu_threads = 3;
+    const double gpu_s = std::max((double)max_blob_bytes / chain, (double)total_bytes / pcie) + 0.002;
+    const double cpu_s = std::max((double)max_blob_bytes / core, (double)total_bytes / (core * cpu_threads));
+    return gpu_s < cpu_s ? 1 : 0;
 }
 
 // ---- digest strings -------------------------------------------------------------------------------
@@ -877,48 +769,51 @@ int mxd_tree_shape(uint64_t size, const mxd_tree_params* tp, uint64_t* counts, i
     return lv;
 }
 
-int mxd_dev_sha256_segments(mxd_ctx* c, int dev, const void* d_data, uint64_t nbytes, uint64_t seg, void* d_out, void* stream) {
-    if (!c || dev < 0 || dev >= (int)c->devs.size() || seg == 0 || !d_out) return fail(MXD_ERR_INVALID, "dev_sha256_segments: bad arguments");
-    DeviceGuard guard(c->devs[dev]->ordinal);
-    return enqueue_segments(c, static_cast<const uint8_t*>(d_data), nbytes, seg, static_cast<uint8_t*>(d_out), (cudaStream_t)stream);
+#define DEV_ARGS_OK(h, dev) (handle_ok(h) && (dev) >= 0 && (dev) < (int)(h)->core->devs.size())
+
+int mxd_dev_sha256_segments(mxd_ctx* h, int dev, const void* d_data, uint64_t nbytes, uint64_t seg, void* d_out, void* stream) {
+    if (!DEV_ARGS_OK(h, dev) || seg == 0 || !d_out) return fail(MXD_ERR_INVALID, "dev_sha256_segments: bad arguments");
+    DeviceGuard guard(h->core->devs[dev]->ordinal);
+    return enqueue_segments(h->core, static_cast<const uint8_t*>(d_data), nbytes, seg, static_cast<uint8_t*>(d_out), (cudaStream_t)stream);
 }
 
-int mxd_dev_sha256_batch(mxd_ctx* c, int dev, const mxd_span* d_spans, uint64_t n, void* d_out, void* stream) {
-    if (!c || dev < 0 || dev >= (int)c->devs.size() || (n && (!d_spans || !d_out))) return fail(MXD_ERR_INVALID, "dev_sha256_batch: bad arguments");
+int mxd_dev_sha256_batch(mxd_ctx* h, int dev, const mxd_span* d_spans, uint64_t n, void* d_out, void* stream) {
+    if (!DEV_ARGS_OK(h, dev) || (n && (!d_spans || !d_out))) return fail(MXD_ERR_INVALID, "dev_sha256_batch: bad arguments");
     if (n == 0) return MXD_OK;
-    DeviceGuard guard(c->devs[dev]->ordinal);
+    DeviceGuard guard(h->core->devs[dev]->ordinal);
     mxd::MsgJob j{};
     j.spans = d_spans; j.nmsg = n; j.out = static_cast<uint8_t*>(d_out); j.finalize = 1; j.one = 1;
     MXD_CUDA(mxd::launch_sha256(j, (cudaStream_t)stream));
-    c->launches++;
+    h->core->launches++;
     return MXD_OK;
 }
 
-int mxd_dev_tree_chunks(mxd_ctx* c, int dev, const void* d_piece, uint64_t nbytes, const mxd_tree_params* tp,
+int mxd_dev_tree_chunks(mxd_ctx* h, int dev, const void* d_piece, uint64_t nbytes, const mxd_tree_params* tp,
                         void* d_chunk_digests, void* stream) {
     Tree t;
-    if (!c || dev < 0 || dev >= (int)c->devs.size() || !tree_resolve(tp, &t) || !d_chunk_digests)
+    if (!DEV_ARGS_OK(h, dev) || !tree_resolve(tp, &t) || !d_chunk_digests)
         return fail(MXD_ERR_INVALID, "dev_tree_chunks: bad arguments");
-    DeviceGuard guard(c->devs[dev]->ordinal);
-    return enqueue_tree_chunks(c, t, static_cast<const uint8_t*>(d_piece), nbytes, static_cast<uint8_t*>(d_chunk_digests),
+    DeviceGuard guard(h->core->devs[dev]->ordinal);
+    return enqueue_tree_chunks(h->core, t, static_cast<const uint8_t*>(d_piece), nbytes, static_cast<uint8_t*>(d_chunk_digests),
                                (cudaStream_t)stream);
 }
 
-int mxd_dev_tree_finish(mxd_ctx* c, int dev, const void* d_chunk_digests, uint64_t nchunks, uint64_t size,
+int mxd_dev_tree_finish(mxd_ctx* h, int dev, const void* d_chunk_digests, uint64_t nchunks, uint64_t size,
                         const mxd_tree_params* tp, void* d_root, void* stream) {
     Tree t;
-    if (!c || dev < 0 || dev >= (int)c->devs.size() || !tree_resolve(tp, &t) || !d_chunk_digests || !d_root || nchunks == 0)
+    if (!DEV_ARGS_OK(h, dev) || !tree_resolve(tp, &t) || !d_chunk_digests || !d_root || nchunks == 0)
         return fail(MXD_ERR_INVALID, "dev_tree_finish: bad arguments");
-    DeviceGuard guard(c->devs[dev]->ordinal);
-    return enqueue_tree_finish(c, t, static_cast<const uint8_t*>(d_chunk_digests), nchunks, size,
+    DeviceGuard guard(h->core->devs[dev]->ordinal);
+    return enqueue_tree_finish(h->core, t, static_cast<const uint8_t*>(d_chunk_digests), nchunks, size,
                                static_cast<uint8_t*>(d_root), (cudaStream_t)stream);
 }
 
-int mxd_dev_tree_digest(mxd_ctx* c, int dev, const void* d_data, uint64_t size, const mxd_tree_params* tp,
+int mxd_dev_tree_digest(mxd_ctx* h, int dev, const void* d_data, uint64_t size, const mxd_tree_params* tp,
                         void* d_chunk_digests, void* d_root, void* stream) {
     Tree t;
-    if (!c || dev < 0 || dev >= (int)c->devs.size() || !tree_resolve(tp, &t) || !d_root)
+    if (!DEV_ARGS_OK(h, dev) || !tree_resolve(tp, &t) || !d_root)
         return fail(MXD_ERR_INVALID, "dev_tree_digest: bad arguments");
+    Core* c = h->core;
     DeviceGuard guard(c->devs[dev]->ordinal);
     cudaStream_t st = (cudaStream_t)stream;
     const uint64_t nchunks = size ? (size + t.chunk - 1) / t.chunk : 1;
@@ -931,26 +826,29 @@ int mxd_dev_tree_digest(mxd_ctx* c, int dev, const void* d_data, uint64_t size, 
     return rc;
 }
 
-int mxd_dev_compare(mxd_ctx* c, int dev, const void* d_got, const void* d_want, uint64_t n, void* d_ok, void* stream) {
-    if (!c || dev < 0 || dev >= (int)c->devs.size() || (n && (!d_got || !d_want || !d_ok))) return fail(MXD_ERR_INVALID, "dev_compare: bad arguments");
-    DeviceGuard guard(c->devs[dev]->ordinal);
+int mxd_dev_compare(mxd_ctx* h, int dev, const void* d_got, const void* d_want, uint64_t n, void* d_ok, void* stream) {
+    if (!DEV_ARGS_OK(h, dev) || (n && (!d_got || !d_want || !d_ok))) return fail(MXD_ERR_INVALID, "dev_compare: bad arguments");
+    DeviceGuard guard(h->core->devs[dev]->ordinal);
     MXD_CUDA(mxd::launch_compare(static_cast<const uint8_t*>(d_got), static_cast<const uint8_t*>(d_want), n,
                                  static_cast<uint8_t*>(d_ok), (cudaStream_t)stream));
-    if (n) c->launches++;
+    if (n) h->core->launches++;
     return MXD_OK;
 }
 
-int mxd_dev_gen_fill(mxd_ctx* c, int dev, void* d_dst, uint64_t offset, uint64_t n, uint64_t seed, void* stream) {
-    if (!c || dev < 0 || dev >= (int)c->devs.size() || (n && !d_dst)) return fail(MXD_ERR_INVALID, "dev_gen_fill: bad arguments");
-    DeviceGuard guard(c->devs[dev]->ordinal);
+int mxd_dev_gen_fill(mxd_ctx* h, int dev, void* d_dst, uint64_t offset, uint64_t n, uint64_t seed, void* stream) {
+    if (!DEV_ARGS_OK(h, dev) || (n && !d_dst)) return fail(MXD_ERR_INVALID, "dev_gen_fill: bad arguments");
+    DeviceGuard guard(h->core->devs[dev]->ordinal);
     MXD_CUDA(mxd::launch_gen_fill(d_dst, offset, n, seed, (cudaStream_t)stream));
-    if (n) c->launches++;
+    if (n) h->core->launches++;
     return MXD_OK;
 }
 
-int mxd_tree_chunks(mxd_ctx* c, const void* piece, uint64_t nbytes, const mxd_tree_params* tp, uint8_t* out) {
+int mxd_tree_chunks(mxd_ctx* h, const void* piece, uint64_t nbytes, const mxd_tree_params* tp, uint8_t* out) {
     Tree t;
-    if (!c || !tree_resolve(tp, &t) || !out || (nbytes && !piece)) return fail(MXD_ERR_INVALID, "tree_chunks: bad arguments");
+    if (!handle_ok(h) || !tree_resolve(tp, &t) || !out || (nbytes && !piece)) return fail(MXD_ERR_INVALID, "tree_chunks: bad arguments");
+    Core* c = h->core;
+    const CancelScope cs(h);
+    if (cs.canceled()) return fail(MXD_ERR_CANCELED, "canceled");
     const uint64_t nchunks = nbytes ? (nbytes + t.chunk - 1) / t.chunk : 1;
     int ord = -1;
     const MemKind kind = classify(piece, &ord);
@@ -973,46 +871,49 @@ int mxd_tree_chunks(mxd_ctx* c, const void* piece, uint64_t nbytes, const mxd_tr
         return rc;
     }
     Source src; src.mem = static_cast<const uint8_t*>(piece); src.pinned = (kind == MemKind::Pinned);
-    return host_tree_chunks_all(c, t, src, nbytes, out);
+    return host_tree_chunks_all(c, cs, t, src, nbytes, out);
 }
 
-int mxd_tree_finish(mxd_ctx* c, const uint8_t* chunk_digests, uint64_t nchunks, uint64_t size, const mxd_tree_params* tp,
+int mxd_tree_finish(mxd_ctx* h, const uint8_t* chunk_digests, uint64_t nchunks, uint64_t size, const mxd_tree_params* tp,
                     uint8_t root[32]) {
     Tree t;
-    if (!c || !tree_resolve(tp, &t) || !chunk_digests || !root || nchunks == 0) return fail(MXD_ERR_INVALID, "tree_finish: bad arguments");
+    if (!handle_ok(h) || !tree_resolve(tp, &t) || !chunk_digests || !root || nchunks == 0) return fail(MXD_ERR_INVALID, "tree_finish: bad arguments");
     const uint64_t expect = size ? (size + t.chunk - 1) / t.chunk : 1;
     if (expect != nchunks) return fail(MXD_ERR_INVALID, "tree_finish: nchunks does not match size/chunk");
-    return host_tree_finish(c, c->devs[0], t, chunk_digests, nchunks, size, root);
+    return host_tree_finish(h->core, h->core->devs[0], t, chunk_digests, nchunks, size, root);
 }
 
-int mxd_tree_digest(mxd_ctx* c, const void* data, uint64_t size, const mxd_tree_params* tp, uint8_t* chunk_digests,
+int mxd_tree_digest(mxd_ctx* h, const void* data, uint64_t size, const mxd_tree_params* tp, uint8_t* chunk_digests,
                     uint64_t* nchunks_out, uint8_t root[32]) {
     Tree t;
-    if (!c || !tree_resolve(tp, &t) || !root || (size && !data)) return fail(MXD_ERR_INVALID, "tree_digest: bad arguments");
+    if (!handle_ok(h) || !tree_resolve(tp, &t) || !root || (size && !data)) return fail(MXD_ERR_INVALID, "tree_digest: bad arguments");
     const uint64_t nchunks = size ? (size + t.chunk - 1) / t.chunk : 1;
     std::vector<uint8_t> tmp;
     uint8_t* chunks = chunk_digests;
     if (!chunks) { tmp.resize(nchunks * 32); chunks = tmp.data(); }
-    int rc = mxd_tree_chunks(c, data, size, tp, chunks);
+    int rc = mxd_tree_chunks(h, data, size, tp, chunks);
     if (rc != MXD_OK) return rc;
     if (nchunks_out) *nchunks_out = nchunks;
-    return host_tree_finish(c, c->devs[0], t, chunks, nchunks, size, root);
+    return host_tree_finish(h->core, h->core->devs[0], t, chunks, nchunks, size, root);
 }
 
-int mxd_tree_digest_file(mxd_ctx* c, const char* path, const mxd_tree_params* tp, uint8_t* chunk_digests,
+int mxd_tree_digest_file(mxd_ctx* h, const char* path, const mxd_tree_params* tp, uint8_t* chunk_digests,
                          uint64_t cap_chunks, uint64_t* nchunks_out, uint64_t* size_out, uint8_t root[32]) {
-    return mxd_tree_digest_file_tee(c, path, tp, chunk_digests, cap_chunks, nchunks_out, size_out, root, nullptr, nullptr);
+    return mxd_tree_digest_file_tee(h, path, tp, chunk_digests, cap_chunks, nchunks_out, size_out, root, nullptr, nullptr);
 }
 
-int mxd_tree_digest_file_tee(mxd_ctx* c, const char* path, const mxd_tree_params* tp, uint8_t* chunk_digests,
+int mxd_tree_digest_file_tee(mxd_ctx* h, const char* path, const mxd_tree_params* tp, uint8_t* chunk_digests,
                              uint64_t cap_chunks, uint64_t* nchunks_out, uint64_t* size_out, uint8_t root[32],
                              mxd_sink_fn sink, void* user) {
     Tree t;
-    if (!c || !path || !tree_resolve(tp, &t) || !root) return fail(MXD_ERR_INVALID, "tree_digest_file: bad arguments");
+    if (!handle_ok(h) || !path || !tree_resolve(tp, &t) || !root) return fail(MXD_ERR_INVALID, "tree_digest_file: bad arguments");
+    const CancelScope cs(h);
+    if (cs.canceled()) return fail(MXD_ERR_CANCELED, "canceled");
     int fd = open(path, O_RDONLY | O_CLOEXEC);
     if (fd < 0) return fail(MXD_ERR_IO, std::string("open ") + path + ": " + strerror(errno));
     struct stat st;
     if (fstat(fd, &st) != 0) { int e = errno; close(fd); errno = e; return fail(MXD_ERR_IO, std::string("fstat: ") + strerror(e)); }
+    if (S_ISDIR(st.st_mode)) { close(fd); return fail(MXD_ERR_IO, std::string("read ") + path + ": is a directory"); }
     const uint64_t size = (uint64_t)st.st_size;
     const uint64_t nchunks = size ? (size + t.chunk - 1) / t.chunk : 1;
     if (size_out) *size_out = size;
@@ -1022,17 +923,49 @@ int mxd_tree_digest_file_tee(mxd_ctx* c, const char* path, const mxd_tree_params
     uint8_t* chunks = chunk_digests;
     if (!chunks) { tmp.resize(nchunks * 32); chunks = tmp.data(); }
     Source src; src.fd = fd; src.sink = sink; src.sink_user = user;
-    int rc = host_tree_chunks_all(c, t, src, size, chunks);
+    int rc = host_tree_chunks_all(h->core, cs, t, src, size, chunks);
     close(fd);
     if (rc != MXD_OK) return rc;
-    return host_tree_finish(c, c->devs[0], t, chunks, nchunks, size, root);
+    return host_tree_finish(h->core, h->core->devs[0], t, chunks, nchunks, size, root);
 }
 
 // ---- whole-message digests ---------------------------------------------------------------------------
-int mxd_sha256_batch(mxd_ctx* c, const mxd_span* spans, uint64_t n, uint8_t* out) {
-    if (!c || (n && (!spans || !out))) return fail(MXD_ERR_INVALID, "sha256_batch: bad arguments");
-    if (n == 0) return MXD_OK;
-    // device-resident spans: one launch, no staging
+// device-resident spans: one launch, no staging; optionally compared with `want` on the device (k_compare)
+static int dev_spans_digest(mxd_ctx* h, int first_ord, const mxd_span* spans, uint64_t n, uint8_t* out, const uint8_t* want, uint8_t* ok) {
+    Core* c = h->core;
+    const int di = dev_index_of(c, first_ord);
+    if (di < 0) return fail(MXD_ERR_INVALID, "sha256_batch: data lives on a device this context does not drive");
+    DevState* d = c->devs[di];
+    DeviceGuard guard(d->ordinal);
+    cudaStream_t st = d->compute;
+    std::lock_guard<std::mutex> lk(d->mu);
+    uint8_t* d_buf = nullptr;   // [spans][digests][want][ok]
+    const uint64_t o_dig = n * sizeof(mxd_span), o_want = o_dig + n * 32, o_ok = o_want + n * 32;
+    MXD_CUDA(cudaMallocAsync(&d_buf, o_ok + n, st));
+    int rc = MXD_OK;
+    uint64_t total = 0; for (uint64_t i = 0; i < n; ++i) total += spans[i].len;
+    cudaError_t e = cudaMemcpyAsync(d_buf, spans, n * sizeof(mxd_span), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        mxd::MsgJob j{};
+        j.spans = d_buf; j.nmsg = n; j.out = d_buf + o_dig; j.finalize = 1; j.one = 1;
+        e = mxd::launch_sha256(j, st);
+        c->launches++; c->bytes_hashed += total;
+    }
+    if (e == cudaSuccess && want) {
+        e = cudaMemcpyAsync(d_buf + o_want, want, n * 32, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = mxd::launch_compare(d_buf + o_dig, d_buf + o_want, n, d_buf + o_ok, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(ok, d_buf + o_ok, n, cudaMemcpyDeviceToHost, st);
+        c->launches++; c->d2h += n;
+    }
+    if (e == cudaSuccess && out) { e = cudaMemcpyAsync(out, d_buf + o_dig, n * 32, cudaMemcpyDeviceToHost, st); c->d2h += n * 32; }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = fail(MXD_ERR_CUDA, cudaGetErrorString(e));
+    cudaFreeAsync(d_buf, st);
+    return rc;
+}
+
+// classify a span list: all host, or all on one device
+static int spans_kind(const mxd_span* spans, uint64_t n, bool* on_device, int* ord_out) {
     int ord = -1, first_ord = -1;
     bool all_dev = true, any_dev = false;
     for (uint64_t i = 0; i < n; ++i) {
@@ -1044,222 +977,129 @@ int mxd_sha256_batch(mxd_ctx* c, const mxd_span* spans, uint64_t n, uint8_t* out
         } else all_dev = false;
     }
     if (any_dev && !all_dev) return fail(MXD_ERR_INVALID, "sha256_batch: mixing host and device spans");
-    if (any_dev) {
-        const int di = dev_index_of(c, first_ord);
-        if (di < 0) return fail(MXD_ERR_INVALID, "sha256_batch: data lives on a device this context does not drive");
-        DevState* d = c->devs[di];
-        std::lock_guard<std::mutex> lk(d->mu);
-        DeviceGuard guard(d->ordinal);
-        uint8_t* d_buf = nullptr;
-        MXD_CUDA(cudaMallocAsync(&d_buf, n * (sizeof(mxd_span) + 32), d->compute));
-        int rc = MXD_OK;
-        uint64_t total = 0; for (uint64_t i = 0; i < n; ++i) total += spans[i].len;
-        cudaError_t e = cudaMemcpyAsync(d_buf, spans, n * sizeof(mxd_span), cudaMemcpyHostToDevice, d->compute);
-        if (e == cudaSuccess) {
-            mxd::MsgJob j{};
-            j.spans = d_buf; j.nmsg = n; j.out = d_buf + n * sizeof(mxd_span); j.finalize = 1; j.one = 1;
-            e = mxd::launch_sha256(j, d->compute);
-            c->launches++; c->bytes_hashed += total;
-        }
-        if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_buf + n * sizeof(mxd_span), n * 32, cudaMemcpyDeviceToHost, d->compute);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(d->compute);
-        if (e != cudaSuccess) rc = fail(MXD_ERR_CUDA, cudaGetErrorString(e));
-        c->d2h += n * 32;
-        cudaFreeAsync(d_buf, d->compute);
-        return rc;
-    }
-    LockstepInput in;
-    in.src.resize(n); in.len.resize(n);
-    for (uint64_t i = 0; i < n; ++i) { in.src[i].mem = static_cast<const uint8_t*>(spans[i].ptr); in.len[i] = spans[i].len; }
-    return lockstep_digest_all(c, in, out);
+    *on_device = any_dev; *ord_out = first_ord;
+    return MXD_OK;
 }
 
-int mxd_sha256(mxd_ctx* c, const void* data, uint64_t n, uint8_t out[32]) {
-    if (!c || !out || (n && !data)) return fail(MXD_ERR_INVALID, "sha256: bad arguments");
-    mxd_span sp{data, n};
-    return mxd_sha256_batch(c, &sp, 1, out);
-}
-
-int mxd_sha256_files(mxd_ctx* c, const char* const* paths, uint64_t n, uint8_t* out, uint64_t* sizes) {
-    if (!c || (n && (!paths || !out))) return fail(MXD_ERR_INVALID, "sha256_files: bad arguments");
-    if (n == 0) return MXD_OK;
-    LockstepInput in; std::vector<int> fds;
-    int rc = open_files(paths, n, &in, &fds);
+static int first_bad(const std::vector<StreamReq>& reqs, int rc) {
     if (rc != MXD_OK) return rc;
-    if (sizes) for (uint64_t i = 0; i < n; ++i) sizes[i] = in.len[i];
-    rc = lockstep_digest_all(c, in, out);
-    for (int fd : fds) close(fd);
-    return rc;
+    for (auto& r : reqs) if (r.status != MXD_OK) return fail(r.status, r.error);
+    return MXD_OK;
 }
 
-int mxd_sha256_file_parts(mxd_ctx* c, const char* path, const mxd_part* parts, uint64_t n, uint8_t* out) {
-    if (!c || !path || (n && (!parts || !out))) return fail(MXD_ERR_INVALID, "sha256_file_parts: bad arguments");
+int mxd_sha256_batch(mxd_ctx* h, const mxd_span* spans, uint64_t n, uint8_t* out) {
+    if (!handle_ok(h) || (n && (!spans || !out))) return fail(MXD_ERR_INVALID, "sha256_batch: bad arguments");
     if (n == 0) return MXD_OK;
-    int fd = open(path, O_RDONLY | O_CLOEXEC);
-    if (fd < 0) return fail(MXD_ERR_IO, std::string("open ") + path + ": " + strerror(errno));
-    struct stat st;
-    if (fstat(fd, &st) != 0) { int e = errno; close(fd); errno = e; return fail(MXD_ERR_IO, std::string("fstat: ") + strerror(e)); }
-    LockstepInput in;
-    in.src.resize(n); in.len.resize(n);
+    bool on_dev = false; int ord = -1;
+    int rc = spans_kind(spans, n, &on_dev, &ord);
+    if (rc != MXD_OK) return rc;
+    if (on_dev) return dev_spans_digest(h, ord, spans, n, out, nullptr, nullptr);
+    std::vector<StreamReq> reqs(n);
+    for (uint64_t i = 0; i < n; ++i) { reqs[i].mem = static_cast<const uint8_t*>(spans[i].ptr); reqs[i].size = spans[i].len; reqs[i].whole_out = out + 32 * i; }
+    return first_bad(reqs, svc_run(h, reqs));
+}
+
+int mxd_sha256(mxd_ctx* h, const void* data, uint64_t n, uint8_t out[32]) {
+    if (!handle_ok(h) || !out || (n && !data)) return fail(MXD_ERR_INVALID, "sha256: bad arguments");
+    mxd_span sp{data, n};
+    return mxd_sha256_batch(h, &sp, 1, out);
+}
+
+int mxd_sha256_file_jobs(mxd_ctx* h, mxd_file_job* jobs, uint64_t n) {
+    if (!handle_ok(h) || (n && !jobs)) return fail(MXD_ERR_INVALID, "sha256_file_jobs: bad arguments");
+    std::vector<StreamReq> reqs(n);
     for (uint64_t i = 0; i < n; ++i) {
-        if (parts[i].offset < 0 || parts[i].length < 0 || (uint64_t)parts[i].offset + (uint64_t)parts[i].length > (uint64_t)st.st_size) {
-            close(fd);
-            return fail(MXD_ERR_IO, "sha256_file_parts: part " + std::to_string(i) + " lies outside the file");
+        mxd_file_job& jb = jobs[i];
+        jb.status = MXD_OK; jb.size = 0;
+        if (!jb.path || !jb.out || (jb.nranges && !jb.ranges)) return fail(MXD_ERR_INVALID, "sha256_file_jobs: job " + std::to_string(i) + " has a null path/out/ranges");
+        reqs[i].path = jb.path; reqs[i].sink = jb.sink; reqs[i].sink_user = jb.sink_user;
+        if (jb.nranges == 0) reqs[i].whole_out = jb.out;
+        for (uint64_t k = 0; k < jb.nranges; ++k) {
+            if (jb.ranges[k].offset < 0 || jb.ranges[k].length < 0) return fail(MXD_ERR_INVALID, "sha256_file_jobs: negative range");
+            reqs[i].ranges.push_back({(uint64_t)jb.ranges[k].offset, (uint64_t)jb.ranges[k].length, jb.out + 32 * k});
         }
-        in.src[i].fd = fd; in.src[i].base = (uint64_t)parts[i].offset; in.len[i] = (uint64_t)parts[i].length;
     }
-    int rc = lockstep_digest_all(c, in, out);
-    close(fd);
+    int rc = svc_run(h, reqs);
+    for (uint64_t i = 0; i < n; ++i) { jobs[i].status = reqs[i].status; jobs[i].size = reqs[i].size; }
+    return first_bad(reqs, rc);
+}
+
+int mxd_sha256_files(mxd_ctx* h, const char* const* paths, uint64_t n, uint8_t* out, uint64_t* sizes) {
+    if (!handle_ok(h) || (n && (!paths || !out))) return fail(MXD_ERR_INVALID, "sha256_files: bad arguments");
+    if (n == 0) return MXD_OK;
+    std::vector<mxd_file_job> jobs(n);
+    for (uint64_t i = 0; i < n; ++i) { jobs[i] = mxd_file_job{}; jobs[i].path = paths[i]; jobs[i].out = out + 32 * i; }
+    int rc = mxd_sha256_file_jobs(h, jobs.data(), n);
+    if (sizes) for (uint64_t i = 0; i < n; ++i) sizes[i] = jobs[i].size;
     return rc;
 }
 
-int mxd_sha256_file(mxd_ctx* c, const char* path, uint8_t out[32], uint64_t* size) {
+int mxd_sha256_file_ranges(mxd_ctx* h, const char* path, const mxd_part* ranges, uint64_t n, uint8_t* out, uint64_t* size,
+                           mxd_sink_fn sink, void* user) {
+    if (!handle_ok(h) || !path || (n && (!ranges || !out))) return fail(MXD_ERR_INVALID, "sha256_file_ranges: bad arguments");
+    if (n == 0 && !sink) return MXD_OK;
+    uint8_t dummy[32];
+    mxd_file_job jb{};
+    jb.path = path; jb.ranges = ranges; jb.nranges = n; jb.out = n ? out : dummy; jb.sink = sink; jb.sink_user = user;
+    mxd_part none{0, 0};
+    if (n == 0) { jb.ranges = &none; jb.nranges = 1; }     // tee only: hash an empty range
+    int rc = mxd_sha256_file_jobs(h, &jb, 1);
+    if (size) *size = jb.size;
+    return rc;
+}
+
+int mxd_sha256_file_parts(mxd_ctx* h, const char* path, const mxd_part* parts, uint64_t n, uint8_t* out) {
+    if (!handle_ok(h) || !path || (n && (!parts || !out))) return fail(MXD_ERR_INVALID, "sha256_file_parts: bad arguments");
+    if (n == 0) return MXD_OK;
+    return mxd_sha256_file_ranges(h, path, parts, n, out, nullptr, nullptr, nullptr);
+}
+
+int mxd_sha256_file(mxd_ctx* h, const char* path, uint8_t out[32], uint64_t* size) {
     if (!path) return fail(MXD_ERR_INVALID, "sha256_file: null path");
     const char* paths[1] = {path};
-    return mxd_sha256_files(c, paths, 1, out, size);
+    return mxd_sha256_files(h, paths, 1, out, size);
 }
 
-int mxd_verify_batch(mxd_ctx* c, const mxd_span* spans, const uint8_t* want, uint64_t n, uint8_t* ok) {
-    if (!c || (n && (!spans || !want || !ok))) return fail(MXD_ERR_INVALID, "verify_batch: bad arguments");
+int mxd_verify_batch(mxd_ctx* h, const mxd_span* spans, const uint8_t* want, uint64_t n, uint8_t* ok) {
+    if (!handle_ok(h) || (n && (!spans || !want || !ok))) return fail(MXD_ERR_INVALID, "verify_batch: bad arguments");
+    if (n == 0) return MXD_OK;
+    bool on_dev = false; int ord = -1;
+    int rc = spans_kind(spans, n, &on_dev, &ord);
+    if (rc != MXD_OK) return rc;
+    if (on_dev) return dev_spans_digest(h, ord, spans, n, nullptr, want, ok);   // digests never leave the device
     std::vector<uint8_t> got(n * 32);
-    int rc = mxd_sha256_batch(c, spans, n, got.data());
+    rc = mxd_sha256_batch(h, spans, n, got.data());
     if (rc != MXD_OK) return rc;
     for (uint64_t i = 0; i < n; ++i) ok[i] = memcmp(&got[32 * i], want + 32 * i, 32) == 0;
     return MXD_OK;
 }
 
-int mxd_verify_files(mxd_ctx* c, const char* const* paths, const uint8_t* want, uint64_t n, uint8_t* ok) {
-    if (!c || (n && (!paths || !want || !ok))) return fail(MXD_ERR_INVALID, "verify_files: bad arguments");
+int mxd_verify_files(mxd_ctx* h, const char* const* paths, const uint8_t* want, uint64_t n, uint8_t* ok) {
+    if (!handle_ok(h) || (n && (!paths || !want || !ok))) return fail(MXD_ERR_INVALID, "verify_files: bad arguments");
     std::vector<uint8_t> got(n * 32);
-    int rc = mxd_sha256_files(c, paths, n, got.data(), nullptr);
+    int rc = mxd_sha256_files(h, paths, n, got.data(), nullptr);
     if (rc != MXD_OK) return rc;
     for (uint64_t i = 0; i < n; ++i) ok[i] = memcmp(&got[32 * i], want + 32 * i, 32) == 0;
     return MXD_OK;
 }
 
 // ---- pinned memory -----------------------------------------------------------------------------------
-int mxd_host_alloc(mxd_ctx* c, void** out, uint64_t nbytes) {
-    if (!c || !out) return fail(MXD_ERR_INVALID, "host_alloc: bad arguments");
-    LocalCpuScope numa(c->devs[0]->ordinal);   // place the pages next to the (first) device that will read them
+int mxd_host_alloc(mxd_ctx* h, void** out, uint64_t nbytes) {
+    if (!handle_ok(h) || !out) return fail(MXD_ERR_INVALID, "host_alloc: bad arguments");
+    LocalCpuScope numa(h->core->devs[0]->ordinal);   // place the pages next to the (first) device that will read them
     MXD_CUDA(cudaHostAlloc(out, nbytes, cudaHostAllocPortable));
     return MXD_OK;
 }
 void mxd_host_free(mxd_ctx*, void* p) { if (p) cudaFreeHost(p); }
-int mxd_host_register(mxd_ctx* c, void* p, uint64_t nbytes) {
-    if (!c || !p) return fail(MXD_ERR_INVALID, "host_register: bad arguments");
+int mxd_host_register(mxd_ctx* h, void* p, uint64_t nbytes) {
+    if (!handle_ok(h) || !p) return fail(MXD_ERR_INVALID, "host_register: bad arguments");
     MXD_CUDA(cudaHostRegister(p, nbytes, cudaHostRegisterPortable));
     return MXD_OK;
 }
-int mxd_host_unregister(mxd_ctx* c, void* p) {
-    if (!c || !p) return fail(MXD_ERR_INVALID, "host_unregister: bad arguments");
+int mxd_host_unregister(mxd_ctx* h, void* p) {
+    if (!handle_ok(h) || !p) return fail(MXD_ERR_INVALID, "host_unregister: bad arguments");
     MXD_CUDA(cudaHostUnregister(p));
     return MXD_OK;
-}
-
-}  // extern "C"
-
-// ---- incremental hasher (hash.Hash shape, helper.go:46-49) --------------------------------------------
-// Writes accumulate in a pinned buffer; every full buffer advances the chain on the GPU (state
-// stays in device memory).  Sum hashes the unflushed tail with finalize on a scratch copy, so the
-// running state is untouched, as Go's Sum requires.
-struct mxd_hasher {
-    mxd_ctx* ctx = nullptr;
-    DevState* dev = nullptr;
-    uint8_t* h_buf = nullptr;  // pinned
-    uint8_t* d_buf = nullptr;
-    uint32_t* d_state = nullptr;
-    uint8_t* d_out = nullptr;
-    uint64_t cap = 0, fill = 0, absorbed = 0;
-    std::mutex mu;
-};
-
-namespace {
-constexpr uint64_t kHasherBuf = 4ull << 20;
-
-int hasher_launch(mxd_hasher* h, uint64_t nbytes, int finalize, uint32_t* state, uint8_t* d_out) {
-    mxd_ctx* c = h->ctx;
-    cudaStream_t st = h->dev->compute;
-    if (nbytes) MXD_CUDA(cudaMemcpyAsync(h->d_buf, h->h_buf, nbytes, cudaMemcpyHostToDevice, st));
-    mxd::MsgJob j{};
-    j.base = h->d_buf; j.nbytes = nbytes; j.seg = nbytes ? nbytes : 64; j.nmsg = 1;
-    j.out = d_out; j.state = state; j.prefix_all = h->absorbed; j.finalize = finalize; j.one = 1;
-    MXD_CUDA(mxd::launch_sha256(j, st));
-    c->launches++; c->bytes_hashed += nbytes; c->h2d += nbytes;
-    return MXD_OK;
-}
-}  // namespace
-
-extern "C" {
-
-int mxd_hasher_new(mxd_ctx* c, mxd_hasher** out) {
-    if (!c || !out) return fail(MXD_ERR_INVALID, "hasher_new: bad arguments");
-    auto* h = new mxd_hasher();
-    h->ctx = c; h->dev = pick_device(c); h->cap = kHasherBuf;
-    DeviceGuard guard(h->dev->ordinal);
-    cudaError_t e = cudaHostAlloc(&h->h_buf, h->cap, cudaHostAllocPortable);
-    if (e == cudaSuccess) e = cudaMalloc(&h->d_buf, h->cap);
-    if (e == cudaSuccess) e = cudaMalloc(&h->d_state, 64);
-    if (e == cudaSuccess) e = cudaMalloc(&h->d_out, 32);
-    if (e == cudaSuccess) e = cudaMemcpy(h->d_state, kIVHost, 32, cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) { int rc = fail(MXD_ERR_CUDA, std::string("hasher_new: ") + cudaGetErrorString(e)); mxd_hasher_free(h); return rc; }
-    *out = h;
-    return MXD_OK;
-}
-
-int mxd_hasher_write(mxd_hasher* h, const void* data, uint64_t n) {
-    if (!h || (n && !data)) return fail(MXD_ERR_INVALID, "hasher_write: bad arguments");
-    std::lock_guard<std::mutex> lk(h->mu);
-    DeviceGuard guard(h->dev->ordinal);
-    const uint8_t* p = static_cast<const uint8_t*>(data);
-    while (n) {
-        const uint64_t take = std::min(n, h->cap - h->fill);
-        memcpy(h->h_buf + h->fill, p, take);
-        h->fill += take; p += take; n -= take;
-        if (h->fill == h->cap) {
-            std::lock_guard<std::mutex> dl(h->dev->mu);
-            int rc = hasher_launch(h, h->cap, 0, h->d_state, h->d_out);
-            if (rc != MXD_OK) return rc;
-            MXD_CUDA(cudaStreamSynchronize(h->dev->compute));  // h_buf is about to be overwritten
-            h->absorbed += h->cap; h->fill = 0;
-        }
-    }
-    return MXD_OK;
-}
-
-int mxd_hasher_sum(mxd_hasher* h, uint8_t out[32]) {
-    if (!h || !out) return fail(MXD_ERR_INVALID, "hasher_sum: bad arguments");
-    std::lock_guard<std::mutex> lk(h->mu);
-    DeviceGuard guard(h->dev->ordinal);
-    std::lock_guard<std::mutex> dl(h->dev->mu);
-    // finalize reads the running state but does not write it back
-    int rc = hasher_launch(h, h->fill, 1, h->d_state, h->d_out);
-    if (rc != MXD_OK) return rc;
-    MXD_CUDA(cudaMemcpyAsync(out, h->d_out, 32, cudaMemcpyDeviceToHost, h->dev->compute));
-    MXD_CUDA(cudaStreamSynchronize(h->dev->compute));
-    h->ctx->d2h += 32;
-    return MXD_OK;
-}
-
-int mxd_hasher_reset(mxd_hasher* h) {
-    if (!h) return fail(MXD_ERR_INVALID, "hasher_reset: null");
-    std::lock_guard<std::mutex> lk(h->mu);
-    DeviceGuard guard(h->dev->ordinal);
-    MXD_CUDA(cudaMemcpy(h->d_state, kIVHost, 32, cudaMemcpyHostToDevice));
-    h->fill = 0; h->absorbed = 0;
-    return MXD_OK;
-}
-
-uint64_t mxd_hasher_size(const mxd_hasher* h) { return h ? h->absorbed + h->fill : 0; }
-
-void mxd_hasher_free(mxd_hasher* h) {
-    if (!h) return;
-    if (h->dev) { DeviceGuard guard(h->dev->ordinal);
-        if (h->h_buf) cudaFreeHost(h->h_buf);
-        if (h->d_buf) cudaFree(h->d_buf);
-        if (h->d_state) cudaFree(h->d_state);
-        if (h->d_out) cudaFree(h->d_out);
-    }
-    delete h;
 }
 
 }  // extern "C"

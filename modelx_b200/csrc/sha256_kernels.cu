@@ -55,45 +55,41 @@ __device__ __forceinline__ void unpack_block(const uint4& v0, const uint4& v1, c
     w[12] = bswap32(v3.x); w[13] = bswap32(v3.y); w[14] = bswap32(v3.z); w[15] = bswap32(v3.w);
 }
 
-// MINB = resident CTAs per SM the register allocator must allow (12 x 64 threads -> 80 registers, 16 -> 63).
-template <int MINB>
-__global__ void __launch_bounds__(kThreads, MINB) k_sha256_lanes(const MsgJob j) {
-    const uint64_t m = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
-    const bool valid = m < j.nmsg;
-    const uint32_t one = j.one;
-
-    // ---- locate this lane's message ------------------------------------------------------
-    const uint8_t* ptr = nullptr;
-    uint64_t len = 0;
-    if (valid) {
-        if (j.base != nullptr) {
-            const uint64_t off = m * j.seg;
-            ptr = j.base + off;
-            len = (off < j.nbytes) ? ((j.nbytes - off < j.seg) ? j.nbytes - off : j.seg) : 0;
-        } else {
-            const DevSpan sp = reinterpret_cast<const DevSpan*>(j.spans)[m];
-            ptr = static_cast<const uint8_t*>(sp.ptr);
-            len = sp.len;
-        }
-    }
-    uint32_t h[8];
-    if (valid && j.state != nullptr) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) h[i] = j.state[8 * m + i];
+// Where message m of a launch lives and what to do with it (shared by both SHA-256 kernels).
+struct Located {
+    const uint8_t* ptr; uint64_t len, prefix;
+    uint32_t sidx, oidx;      // chain-state slot / digest slot
+    int fin; bool live, load_state;
+};
+__device__ __forceinline__ Located locate(const MsgJob& j, uint64_t m) {
+    Located L;
+    L.ptr = nullptr; L.len = 0; L.prefix = j.prefix_all; L.sidx = (uint32_t)m; L.oidx = (uint32_t)m;
+    L.fin = j.finalize; L.live = m < j.nmsg; L.load_state = false;
+    if (!L.live) return L;
+    if (j.descs != nullptr) {
+        const LaneDesc d = j.descs[m];
+        L.ptr = static_cast<const uint8_t*>(d.ptr); L.len = d.len; L.prefix = d.prefix;
+        L.sidx = d.lane; L.oidx = d.oidx;
+        L.fin = (d.ctl & kFinalize) != 0; L.live = (d.ctl & kSkip) == 0;
+        L.load_state = L.live && (d.ctl & kFresh) == 0;
+    } else if (j.base != nullptr) {
+        const uint64_t off = m * j.seg;
+        L.ptr = j.base + off;
+        L.len = (off < j.nbytes) ? ((j.nbytes - off < j.seg) ? j.nbytes - off : j.seg) : 0;
+        L.load_state = j.state != nullptr;
     } else {
-        sha256_iv(h);
+        const DevSpan sp = reinterpret_cast<const DevSpan*>(j.spans)[m];
+        L.ptr = static_cast<const uint8_t*>(sp.ptr);
+        L.len = sp.len;
+        L.load_state = j.state != nullptr;
     }
-    const uint64_t prefix = (j.prefix != nullptr && valid) ? j.prefix[m] : j.prefix_all;
-    const uint64_t nfull = len >> 6;
-    const uint32_t r = (uint32_t)(len & 63u);
-    // blocks this lane compresses: the full ones, then (when finalizing) the padded tail block
-    // and, if the 64-bit length does not fit behind the tail, one more (FIPS 180-4 section 5.1.1).
-    int fin = j.finalize;
-    bool live = valid;
-    if (j.ctl != nullptr && valid) { const uint8_t c = j.ctl[m]; fin = (c == 1); live = (c != 2); }
-    const uint64_t nblk = live ? nfull + (fin ? (r >= 56 ? 2u : 1u) : 0u) : 0;
-    const uint64_t bits = (prefix + len) << 3;
+    return L;
+}
 
+// Run one lane's chain over its message: `nfull` full blocks at ptr, then (nblk > nfull) the padded tail block and,
+// if needed, the length block.  All 32 lanes of the warp must call this together.
+__device__ __forceinline__ void absorb(const uint8_t* ptr, const uint64_t nfull, const uint32_t r, const uint64_t nblk,
+                                       const uint64_t bits, const bool live, uint32_t (&h)[8], const uint32_t one) {
     // Hot loop: when every lane of the warp has a 16-byte aligned message (always true for tree
     // levels) the full blocks run in a straight-line loop of their own: 4 x LDG.128 per block, the
     // next block prefetched into registers while this one is compressed.  Keeping this loop free of
@@ -142,20 +138,46 @@ __global__ void __launch_bounds__(kThreads, MINB) k_sha256_lanes(const MsgJob j)
         sha256_compress(h, w, one);
     }
 
+}
+
+// MINB = resident CTAs per SM the register allocator must allow (12 x 64 threads -> 80 registers, 16 -> 63).
+template <int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) k_sha256_lanes(const MsgJob j) {
+    const uint64_t m = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+    const uint32_t one = j.one;
+    const Located L = locate(j, m);
+    const uint8_t* ptr = L.ptr;
+    const uint64_t len = L.len;
+    const bool live = L.live;
+    const int fin = L.fin;
+    uint32_t h[8];
+    if (L.load_state) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) h[i] = j.state[8 * (uint64_t)L.sidx + i];
+    } else {
+        sha256_iv(h);
+    }
+    const uint64_t nfull = len >> 6;
+    const uint32_t r = (uint32_t)(len & 63u);
+    // blocks this lane compresses: the full ones, then (when finalizing) the padded tail block
+    // and, if the 64-bit length does not fit behind the tail, one more (FIPS 180-4 section 5.1.1).
+    const uint64_t nblk = live ? nfull + (fin ? (r >= 56 ? 2u : 1u) : 0u) : 0;
+    const uint64_t bits = (L.prefix + len) << 3;
+
+    absorb(ptr, nfull, r, nblk, bits, live, h, one);
+
     if (!live) return;
     if (!fin) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) j.state[8 * m + i] = h[i];
+        for (int i = 0; i < 8; ++i) j.state[8 * (uint64_t)L.sidx + i] = h[i];
         return;
     }
     uint4 lo, hi;
     lo.x = bswap32(h[0]); lo.y = bswap32(h[1]); lo.z = bswap32(h[2]); lo.w = bswap32(h[3]);
     hi.x = bswap32(h[4]); hi.y = bswap32(h[5]); hi.z = bswap32(h[6]); hi.w = bswap32(h[7]);
-    uint4* o = reinterpret_cast<uint4*>(j.out + 32 * m);
+    uint4* o = reinterpret_cast<uint4*>(j.out + 32 * (uint64_t)L.oidx);
     o[0] = lo; o[1] = hi;
 }
-
-
 
 // =====================================================================================================
 // k_sha256_chains_coop: few, long chains.  A SHA-256 chain is serial, so when a launch has only a few
@@ -184,30 +206,16 @@ __global__ void __launch_bounds__(64) k_sha256_chains_coop(const MsgJob j) {
     const int lane = threadIdx.x & 31;
     const int role = threadIdx.x >> 5;            // 0 = chain warp, 1 = producer warp
     const uint64_t m = (uint64_t)blockIdx.x * 32 + lane;
-    const bool valid = m < j.nmsg;
     const uint32_t one = j.one;
-
-    const uint8_t* ptr = nullptr;
-    uint64_t len = 0;
-    if (valid) {
-        if (j.base != nullptr) {
-            const uint64_t off = m * j.seg;
-            ptr = j.base + off;
-            len = (off < j.nbytes) ? ((j.nbytes - off < j.seg) ? j.nbytes - off : j.seg) : 0;
-        } else {
-            const DevSpan sp = reinterpret_cast<const DevSpan*>(j.spans)[m];
-            ptr = static_cast<const uint8_t*>(sp.ptr);
-            len = sp.len;
-        }
-    }
-    const uint64_t prefix = (j.prefix != nullptr && valid) ? j.prefix[m] : j.prefix_all;
+    const Located L = locate(j, m);
+    const uint8_t* ptr = L.ptr;
+    const uint64_t len = L.len;
+    const bool live = L.live;
+    const int fin = L.fin;
     const uint64_t nfull = len >> 6;
     const uint32_t r = (uint32_t)(len & 63u);
-    int fin = j.finalize;
-    bool live = valid;
-    if (j.ctl != nullptr && valid) { const uint8_t c = j.ctl[m]; fin = (c == 1); live = (c != 2); }
     const uint64_t nblk = live ? nfull + (fin ? (r >= 56 ? 2u : 1u) : 0u) : 0;
-    const uint64_t bits = (prefix + len) << 3;
+    const uint64_t bits = (L.prefix + len) << 3;
     // both warps iterate to the longest chain of the 32; shorter lanes idle through the barriers
     uint64_t nmax = nblk;
 #pragma unroll
@@ -304,9 +312,9 @@ __global__ void __launch_bounds__(64) k_sha256_chains_coop(const MsgJob j) {
 
     // ---------------- chain warp: 64 rounds per block on W+K from shared memory ------------------------
     uint32_t h[8];
-    if (valid && j.state != nullptr) {
+    if (L.load_state) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) h[i] = j.state[8 * m + i];
+        for (int i = 0; i < 8; ++i) h[i] = j.state[8 * (uint64_t)L.sidx + i];
     } else {
         sha256_iv(h);
     }
@@ -355,43 +363,213 @@ __global__ void __launch_bounds__(64) k_sha256_chains_coop(const MsgJob j) {
     if (!live) return;
     if (!fin) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) j.state[8 * m + i] = h[i];
+        for (int i = 0; i < 8; ++i) j.state[8 * (uint64_t)L.sidx + i] = h[i];
         return;
     }
     uint4 lo, hi;
     lo.x = bswap32(h[0]); lo.y = bswap32(h[1]); lo.z = bswap32(h[2]); lo.w = bswap32(h[3]);
     hi.x = bswap32(h[4]); hi.y = bswap32(h[5]); hi.z = bswap32(h[6]); hi.w = bswap32(h[7]);
-    uint4* o = reinterpret_cast<uint4*>(j.out + 32 * m);
+    uint4* o = reinterpret_cast<uint4*>(j.out + 32 * (uint64_t)L.oidx);
     o[0] = lo; o[1] = hi;
 }
 
-// One thread: the 72-byte root message of modelx.tree.v1 (two blocks with padding).
-__global__ void k_tree_root(uint64_t size, uint64_t leaf, uint32_t fanout, const uint8_t* __restrict__ top,
-                            uint8_t* __restrict__ root, uint32_t one) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    uint8_t msg[128];
-    const char magic[16] = {'m', 'o', 'd', 'e', 'l', 'x', '.', 't', 'r', 'e', 'e', '.', 'v', '1', 0, 0};
-    for (int i = 0; i < 16; ++i) msg[i] = (uint8_t)magic[i];
-    for (int i = 0; i < 8; ++i) { msg[16 + i] = (uint8_t)(size >> (8 * i)); msg[24 + i] = (uint8_t)(leaf >> (8 * i)); }
-    for (int i = 0; i < 4; ++i) { msg[32 + i] = (uint8_t)(fanout >> (8 * i)); msg[36 + i] = 0; }
-    for (int i = 0; i < 32; ++i) msg[40 + i] = top[i];
-    msg[72] = 0x80;
-    for (int i = 73; i < 128; ++i) msg[i] = 0;
-    msg[126] = (uint8_t)((72 * 8) >> 8); msg[127] = (uint8_t)(72 * 8);
-    uint32_t h[8]; sha256_iv(h);
+// SHA-256 of a short message given as `nwords` big-endian 32-bit words (nwords a multiple of 8: concatenated
+// digests), fetched through `word(i)`.  Tree nodes above the leaves: fanout * 8 words, 5 blocks for fanout 8.
+template <typename F>
+__device__ __forceinline__ void sha256_words(F word, const uint32_t nwords, uint32_t (&h)[8], const uint32_t one) {
+    sha256_iv(h);
+    const uint32_t nblk = (nwords * 4u + 9u + 63u) >> 6;
     uint32_t w[16];
-    for (int b = 0; b < 2; ++b) {
+    for (uint32_t b = 0; b < nblk; ++b) {
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-            const uint8_t* q = msg + 64 * b + 4 * k;
-            w[k] = ((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | (uint32_t)q[3];
+            const uint32_t wi = 16u * b + (uint32_t)k;
+            w[k] = wi < nwords ? word(wi) : (wi == nwords ? 0x80000000u : 0u);
         }
+        if (b + 1 == nblk) { w[14] = 0; w[15] = nwords * 32u; }
         sha256_compress(h, w, one);
     }
-    for (int i = 0; i < 8; ++i) {
-        root[4 * i] = (uint8_t)(h[i] >> 24); root[4 * i + 1] = (uint8_t)(h[i] >> 16);
-        root[4 * i + 2] = (uint8_t)(h[i] >> 8); root[4 * i + 3] = (uint8_t)h[i];
+}
+
+__device__ __forceinline__ void store_digest(uint8_t* out, const uint32_t (&h)[8]) {
+    uint4 lo, hi;
+    lo.x = bswap32(h[0]); lo.y = bswap32(h[1]); lo.z = bswap32(h[2]); lo.w = bswap32(h[3]);
+    hi.x = bswap32(h[4]); hi.y = bswap32(h[5]); hi.z = bswap32(h[6]); hi.w = bswap32(h[7]);
+    uint4* o = reinterpret_cast<uint4*>(out);
+    o[0] = lo; o[1] = hi;
+}
+
+// =====================================================================================================
+// k_tree_leaves: the leaf level of modelx.tree.v1 with the first tree levels fused in.
+//
+// Work unit = 64 consecutive leaves = one CTA pass: lane t hashes leaf 64u+t exactly like k_sha256_lanes, the 64
+// digests meet in shared memory and the CTA reduces them through `fused` tree levels (fanout 8: 64 -> 8 -> 1, i.e.
+// one digest per MiB leaves the kernel instead of 64), so levels 1..fused cost no launch, no DRAM round trip and no
+// dependency tail behind the leaf launch.
+//
+// Scheduling (mode 0, large inputs): a grid-scheduled launch ends with a drain in which the CTAs of an SM finish at
+// scattered times and the last leaves run on a nearly empty machine (measured: a constant ~0.33 ms per launch,
+// 2.6 % of a 12.5 GB launch).  Here the grid is exactly one CTA per resident slot (SMs x 12).  Every CTA looks up
+// the SM it landed on (%smid) and takes a slot number there; SM s owns a contiguous share of the units, and its
+// slots walk through that share in aligned rounds: with a units on the SM and 12 slots, q = ceil(a/12) units go to
+// each of kmain = floor(a/q) >= 8 slots and the few left over to one more slot, which finishes early.  All kmain
+// CTAs of an SM share its issue slots evenly, so they end together with >= 16 warps resident until the last block.
+// Placement is not guaranteed by CUDA, so every unit is claimed with an atomic before it is hashed and a second,
+// normally empty launch (mode 2) sweeps up any unit whose slot never showed up.  Results do not depend on who
+// hashes what.  Small inputs (mode 1): one unit per CTA, grid = units.
+// =====================================================================================================
+constexpr uint32_t kMaxSmid = 1024;
+constexpr uint32_t kSchedHeaderWords = 4 + 2 * kMaxSmid;
+
+__global__ void __launch_bounds__(kThreads, 12) k_tree_leaves(const LeafJob j, const uint32_t n_units, const uint32_t nsm,
+                                                              const uint32_t kper, const uint32_t mode) {
+    __shared__ uint32_t dig[2][64][8];
+    __shared__ uint32_t s_info[4];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t one = j.one;
+    uint32_t* const n_seen = j.sched;
+    uint32_t* const sm_slots = j.sched + 4;
+    uint32_t* const sm_dense = sm_slots + kMaxSmid;
+    uint32_t* const claimed = sm_dense + kMaxSmid;
+
+    uint32_t first = 0, stride = 1, count = 0;     // this CTA hashes units first + i*stride, i < count
+    if (mode == 0) {
+        if (tid == 0) {
+            uint32_t smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            uint32_t slot = 0xffffffffu, dense = 0xffffffffu;
+            if (smid < kMaxSmid) {
+                slot = atomicAdd(&sm_slots[smid], 1u);
+                if (slot == 0) {                    // first CTA on this SM: give the SM a dense index
+                    dense = atomicAdd(n_seen, 1u);
+                    atomicExch(&sm_dense[smid], dense + 1u);
+                } else {                            // the slot-0 CTA is already running: its store arrives shortly
+                    uint32_t v;
+                    while ((v = atomicAdd(&sm_dense[smid], 0u)) == 0u) __nanosleep(20);
+                    dense = v - 1u;
+                }
+            }
+            s_info[0] = slot; s_info[1] = dense;
+        }
+        __syncthreads();
+        const uint32_t slot = s_info[0], dense = s_info[1];
+        if (dense < nsm) {
+            uint32_t a = n_units / nsm;
+            const uint32_t rem = n_units % nsm;
+            const uint32_t u0 = dense * a + (dense < rem ? dense : rem);
+            a += dense < rem ? 1u : 0u;
+            const uint32_t q = (a + kper - 1) / kper;
+            const uint32_t kmain = q ? a / q : 0u;
+            if (slot < kmain) { first = u0 + slot; stride = kmain; count = q; }
+            else if (slot == kmain) { first = u0 + kmain * q; stride = 1; count = a - kmain * q; }
+        }
+    } else {
+        first = blockIdx.x; stride = gridDim.x;
+        count = first < n_units ? (n_units - first + stride - 1) / stride : 0u;
     }
+
+    uint32_t span = 1;
+    for (uint32_t lv = 0; lv < j.fused; ++lv) span *= j.fanout;
+
+    for (uint32_t i = 0; i < count; ++i) {
+        const uint32_t u = first + i * stride;
+        if (mode != 1) {
+            __syncthreads();                        // s_info[2] of the previous unit has been read by everyone
+            if (tid == 0) s_info[2] = (mode == 2 && *reinterpret_cast<volatile uint32_t*>(&claimed[u]) != 0u)
+                                          ? 1u : atomicCAS(&claimed[u], 0u, 1u);
+            __syncthreads();
+            if (s_info[2] != 0u) continue;
+        }
+        // ---- lane t: leaf 64u + t --------------------------------------------------------------------
+        const uint64_t leaf_idx = (uint64_t)u * 64u + tid;
+        const bool live = leaf_idx < j.n0;
+        const uint64_t off = leaf_idx * j.leaf;
+        const uint64_t len = (live && off < j.nbytes) ? ((j.nbytes - off < j.leaf) ? j.nbytes - off : j.leaf) : 0;
+        const uint8_t* ptr = j.base + (live ? off : 0);
+        const uint64_t nfull = len >> 6;
+        const uint32_t r = (uint32_t)(len & 63u);
+        const uint64_t nblk = live ? nfull + (r >= 56 ? 2u : 1u) : 0;
+        uint32_t h[8];
+        sha256_iv(h);
+        absorb(ptr, nfull, r, nblk, len << 3, live, h, one);
+        if (j.fused == 0) {
+            if (live) store_digest(j.out + 32 * leaf_idx, h);
+            continue;
+        }
+        // ---- the tree levels that fit inside these 64 leaves, through shared memory -----------------------
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dig[0][tid][k] = h[k];
+        __syncthreads();
+        const uint64_t left = j.n0 - (uint64_t)u * 64u;
+        uint32_t cnt = left < 64u ? (uint32_t)left : 64u;
+        uint32_t cur = 0;
+        for (uint32_t lv = 0; lv < j.fused; ++lv) {
+            const uint32_t nn = (cnt + j.fanout - 1) / j.fanout;
+            if (tid < nn) {
+                const uint32_t have = cnt - tid * j.fanout;
+                const uint32_t nch = have < j.fanout ? have : j.fanout;
+                const uint32_t* src = &dig[cur][tid * j.fanout][0];
+                uint32_t g[8];
+                sha256_words([&](uint32_t wi) { return src[wi]; }, nch * 8u, g, one);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) dig[cur ^ 1][tid][k] = g[k];
+            }
+            __syncthreads();
+            cur ^= 1; cnt = nn;
+        }
+        if (tid < cnt) {
+            uint32_t g[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) g[k] = dig[cur][tid][k];
+            store_digest(j.out + 32 * (((uint64_t)u * 64u) / span + tid), g);
+        }
+        __syncthreads();                            // dig[] is free for the next unit
+    }
+}
+
+// Everything above a short digest list in one CTA: levels while more than one node remains, then the 72-byte root
+// message of modelx.tree.v1 (two blocks with padding).  scratch: two buffers of ceil(n/fanout)*32 bytes.
+__global__ void __launch_bounds__(256) k_tree_top(const uint8_t* __restrict__ in, uint64_t n, const uint32_t fanout,
+                                                  const uint64_t size, const uint64_t leaf, uint8_t* scratch,
+                                                  uint8_t* __restrict__ root, const uint32_t one) {
+    const uint64_t half = ((n + fanout - 1) / fanout) * 32;
+    const uint8_t* cur = in;
+    uint8_t* bufs[2] = {scratch, scratch + half};
+    int which = 0;
+    while (n > 1) {
+        const uint64_t nn = (n + fanout - 1) / fanout;
+        uint8_t* dst = bufs[which];
+        for (uint64_t i = threadIdx.x; i < nn; i += blockDim.x) {
+            const uint64_t have = n - i * fanout;
+            const uint32_t nch = have < fanout ? (uint32_t)have : fanout;
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(cur + i * fanout * 32);
+            uint32_t g[8];
+            sha256_words([&](uint32_t wi) { return bswap32(src[wi]); }, nch * 8u, g, one);
+            store_digest(dst + 32 * i, g);
+        }
+        __syncthreads();
+        cur = dst; which ^= 1; n = nn;
+    }
+    if (threadIdx.x != 0) return;
+    uint32_t m[18];   // the 72-byte root message as big-endian words
+    m[0] = 0x6d6f6465u; m[1] = 0x6c782e74u; m[2] = 0x7265652eu; m[3] = 0x76310000u;   // "modelx.tree.v1\0\0"
+    m[4] = bswap32((uint32_t)size); m[5] = bswap32((uint32_t)(size >> 32));              // LE64(size)
+    m[6] = bswap32((uint32_t)leaf); m[7] = bswap32((uint32_t)(leaf >> 32));              // LE64(leaf)
+    m[8] = bswap32(fanout); m[9] = 0;                                                     // LE32(fanout), LE32(0)
+    const uint32_t* top = reinterpret_cast<const uint32_t*>(cur);
+    for (int k = 0; k < 8; ++k) m[10 + k] = bswap32(top[k]);
+    uint32_t h[8];
+    sha256_iv(h);
+    uint32_t w[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) w[k] = m[k];
+    sha256_compress(h, w, one);
+    w[0] = m[16]; w[1] = m[17]; w[2] = 0x80000000u;
+#pragma unroll
+    for (int k = 3; k < 15; ++k) w[k] = 0;
+    w[15] = 72 * 8;
+    sha256_compress(h, w, one);
+    store_digest(root, h);
 }
 
 __global__ void k_compare(const uint8_t* __restrict__ got, const uint8_t* __restrict__ want, uint64_t n,
@@ -459,9 +637,75 @@ cudaError_t launch_gen_fill(void* dst, uint64_t offset, uint64_t n, uint64_t see
     return cudaGetLastError();
 }
 
-cudaError_t launch_tree_root(uint64_t size, uint64_t leaf, uint32_t fanout, const uint8_t* top, uint8_t* root,
-                             cudaStream_t stream) {
-    k_tree_root<<<1, 32, 0, stream>>>(size, leaf, fanout, top, root, 1u);
+// Resident CTAs per SM of the leaf kernel and the SM count of the current device (cached per device).
+static void leaf_geometry(int* nsm, int* per_sm) {
+    static int cache_sm[64] = {0}, cache_occ[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (cache_sm[dev] == 0) {
+        int sms = 0, occ = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_tree_leaves, kThreads, 0);
+        cache_occ[dev] = occ > 0 ? occ : 1;
+        cache_sm[dev] = sms > 0 ? sms : 1;
+    }
+    *nsm = cache_sm[dev]; *per_sm = cache_occ[dev];
+}
+
+uint32_t leaf_fusable_levels(uint32_t fanout, uint32_t want) {
+    if (getenv("MXD_TUNE_NOFUSE")) return 0;
+    uint32_t lv = 0;
+    uint64_t span = 1;
+    while (lv < want && span * fanout <= 64 && 64 % (span * fanout) == 0) { span *= fanout; ++lv; }
+    return lv;
+}
+
+uint64_t leaf_sched_bytes(uint64_t n0) { return (kSchedHeaderWords + (n0 + 63) / 64) * sizeof(uint32_t); }
+
+cudaError_t launch_tree_leaves(const LeafJob& job, cudaStream_t stream) {
+    const uint64_t units64 = (job.n0 + 63) / 64;
+    if (units64 == 0 || units64 > 0x7fffffffull || job.sched == nullptr) return cudaErrorInvalidValue;
+    const uint32_t n_units = (uint32_t)units64;
+    int nsm = 1, per_sm = 1;
+    leaf_geometry(&nsm, &per_sm);
+    static const int tune = [] { const char* e = getenv("MXD_TUNE_LEAF_SCHED"); return e ? atoi(e) : 0; }();   // 1: always grid-scheduled
+    const uint32_t resident = (uint32_t)nsm * (uint32_t)per_sm;
+    if (tune == 1 || n_units < 2 * resident || (uint32_t)nsm > kMaxSmid) {
+        // small input (or A/B): plain grid, one unit per CTA (mode 1 with grid == units)
+        k_tree_leaves<<<n_units, kThreads, 0, stream>>>(job, n_units, (uint32_t)nsm, (uint32_t)per_sm, 1u);
+        return cudaGetLastError();
+    }
+    cudaError_t e = cudaMemsetAsync(job.sched, 0, leaf_sched_bytes(job.n0), stream);
+    if (e != cudaSuccess) return e;
+    k_tree_leaves<<<resident, kThreads, 0, stream>>>(job, n_units, (uint32_t)nsm, (uint32_t)per_sm, 0u);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    // sweep: hashes whatever unit is still unclaimed (none when every SM received its per_sm CTAs)
+    k_tree_leaves<<<(unsigned)nsm, kThreads, 0, stream>>>(job, n_units, (uint32_t)nsm, (uint32_t)per_sm, 2u);
+    return cudaGetLastError();
+}
+
+// scratch layout: two buffers of ceil(n/fanout)*32 bytes for the wide levels, then 16 KiB for k_tree_top's own
+// ping-pong (at most 512 digests enter it, so at most 256 * 32 bytes per buffer).
+constexpr uint64_t kTopNarrow = 512;
+uint64_t tree_top_scratch_bytes(uint64_t n, uint32_t fanout) { return 2 * (((n + fanout - 1) / fanout) * 32) + 2 * (kTopNarrow / 2) * 32; }
+
+cudaError_t launch_tree_top(const uint8_t* digests, uint64_t n, uint32_t fanout, uint64_t size, uint64_t leaf,
+                            uint8_t* scratch, uint8_t* root, cudaStream_t stream) {
+    if (n == 0 || fanout < 2) return cudaErrorInvalidValue;
+    // wide levels first (thousands of nodes want the whole machine), the narrow rest and the root in one CTA
+    const uint64_t half = ((n + fanout - 1) / fanout) * 32;
+    const uint8_t* cur = digests;
+    int which = 0;
+    while (n > kTopNarrow) {
+        MsgJob j{};
+        j.base = cur; j.nbytes = n * 32; j.seg = 32ull * fanout; j.nmsg = (n + fanout - 1) / fanout;
+        j.out = scratch + (which ? half : 0); j.finalize = 1; j.one = 1;
+        cudaError_t e = launch_sha256(j, stream);
+        if (e != cudaSuccess) return e;
+        cur = j.out; which ^= 1; n = j.nmsg;
+    }
+    k_tree_top<<<1, 256, 0, stream>>>(cur, n, fanout, size, leaf, scratch + 2 * half, root, 1u);
     return cudaGetLastError();
 }
 

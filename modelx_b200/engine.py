@@ -65,6 +65,12 @@ def calc_parts(total: int, partscount: int) -> List[Tuple[int, int]]:
     return [(p.offset, p.length) for p in parts[:partscount]]
 
 
+def batch_pays_off(n_blobs: int, total_bytes: int, max_blob_bytes: int = 0) -> bool:
+    """Routing advice (mxd_batch_pays_off): is hashing these blobs together on the GPU expected to beat the
+    reference's three SHA-NI goroutines?"""
+    return bool(N.load().mxd_batch_pays_off(n_blobs, total_bytes, max_blob_bytes))
+
+
 def server_part_count(size: int, force_multipart: bool = False) -> int:
     """Part count the modelxd S3 store chooses (pkg/registry/store_s3.go:198-203, 273-279)."""
     return int(N.load().mxd_server_part_count(size, 1 if force_multipart else 0))
@@ -83,17 +89,34 @@ def tree_shape(size: int, chunk: int = DEFAULT_CHUNK, leaf: int = DEFAULT_LEAF, 
 class Engine:
     """One process-wide digest engine bound to one or more GPUs."""
 
-    def __init__(self, devices: Optional[Sequence[int]] = None, ring_bytes: int = 0):
-        self._lib = N.load()
+    def __init__(self, devices: Optional[Sequence[int]] = None, ring_bytes: int = 0, lib_path: Optional[str] = None):
+        self._lib = N.load(lib_path)
         self._ctx = C.c_void_p()
+        self._parent = None
         devs = list(devices) if devices is not None else []
         arr = (C.c_int * max(len(devs), 1))(*devs)
-        N.check(self._lib.mxd_open(C.byref(self._ctx), arr if devs else None, len(devs), ring_bytes), "mxd_open")
+        self._check(self._lib.mxd_open(C.byref(self._ctx), arr if devs else None, len(devs), ring_bytes), "mxd_open")
+
+    def _check(self, status: int, where: str):
+        N.check(status, where, self._lib)
+
+    def op(self) -> "Engine":
+        """A new operation on this engine (mxd_op_begin): an Engine-shaped handle sharing the devices whose calls
+        can be canceled on their own with ``.cancel()`` (one Go context, push.go:150-159).  Use as a context manager."""
+        child = object.__new__(Engine)
+        child._lib = self._lib
+        child._ctx = C.c_void_p()
+        child._parent = self
+        self._check(self._lib.mxd_op_begin(self._ctx, C.byref(child._ctx)), "mxd_op_begin")
+        return child
 
     # -- lifecycle ---------------------------------------------------------------------------
     def close(self):
         if self._ctx:
-            self._lib.mxd_close(self._ctx)
+            if self._parent is not None:
+                self._lib.mxd_op_end(self._ctx)
+            else:
+                self._lib.mxd_close(self._ctx)
             self._ctx = C.c_void_p()
 
     def __enter__(self):
@@ -117,16 +140,23 @@ class Engine:
 
     def stats(self) -> dict:
         st = N.Stats()
-        N.check(self._lib.mxd_get_stats(self._ctx, C.byref(st)), "mxd_get_stats")
+        self._check(self._lib.mxd_get_stats(self._ctx, C.byref(st)), "mxd_get_stats")
         return {"kernel_launches": st.kernel_launches, "bytes_hashed": st.bytes_hashed,
-                "h2d_bytes": st.h2d_bytes, "d2h_bytes": st.d2h_bytes}
+                "h2d_bytes": st.h2d_bytes, "d2h_bytes": st.d2h_bytes, "src_bytes_read": st.src_bytes_read,
+                "open_files": st.open_files}
+
+    def trace_enable(self, on: bool = True):
+        self._check(self._lib.mxd_trace_enable(self._ctx, 1 if on else 0), "mxd_trace_enable")
+
+    def trace_dump(self, path: str):
+        self._check(self._lib.mxd_trace_dump(self._ctx, path.encode()), "mxd_trace_dump")
 
     def prof_enable(self, on: bool = True):
-        N.check(self._lib.mxd_prof_enable(self._ctx, 1 if on else 0), "mxd_prof_enable")
+        self._check(self._lib.mxd_prof_enable(self._ctx, 1 if on else 0), "mxd_prof_enable")
 
     def prof_read(self) -> dict:
         ms, n, b = C.c_double(), C.c_uint64(), C.c_uint64()
-        N.check(self._lib.mxd_prof_read(self._ctx, C.byref(ms), C.byref(n), C.byref(b)), "mxd_prof_read")
+        self._check(self._lib.mxd_prof_read(self._ctx, C.byref(ms), C.byref(n), C.byref(b)), "mxd_prof_read")
         return {"kernel_ms": ms.value, "launches": n.value, "bytes": b.value}
 
     def cancel(self):
@@ -135,16 +165,19 @@ class Engine:
     def reset_cancel(self):
         self._lib.mxd_reset_cancel(self._ctx)
 
+    def is_canceled(self) -> bool:
+        return bool(self._lib.mxd_is_canceled(self._ctx))
+
     # -- whole-message digests (reference semantics) --------------------------------------------
     def sha256(self, data) -> bytes:
         addr, n, keep = _buf(data)
         out = (C.c_uint8 * 32)()
-        N.check(self._lib.mxd_sha256(self._ctx, addr, n, out), "mxd_sha256")
+        self._check(self._lib.mxd_sha256(self._ctx, addr, n, out), "mxd_sha256")
         return bytes(out)
 
     def sha256_ptr(self, ptr: int, n: int) -> bytes:
         out = (C.c_uint8 * 32)()
-        N.check(self._lib.mxd_sha256(self._ctx, ptr, n, out), "mxd_sha256")
+        self._check(self._lib.mxd_sha256(self._ctx, ptr, n, out), "mxd_sha256")
         return bytes(out)
 
     def sha256_batch(self, items: Iterable) -> List[bytes]:
@@ -155,7 +188,7 @@ class Engine:
             spans[i].ptr = addr
             spans[i].len = ln
         out = (C.c_uint8 * (32 * max(n, 1)))()
-        N.check(self._lib.mxd_sha256_batch(self._ctx, spans, n, out), "mxd_sha256_batch")
+        self._check(self._lib.mxd_sha256_batch(self._ctx, spans, n, out), "mxd_sha256_batch")
         raw = bytes(out)
         return [raw[32 * i:32 * i + 32] for i in range(n)]
 
@@ -166,14 +199,14 @@ class Engine:
             spans[i].ptr = addr
             spans[i].len = ln
         out = (C.c_uint8 * (32 * max(n, 1)))()
-        N.check(self._lib.mxd_sha256_batch(self._ctx, spans, n, out), "mxd_sha256_batch")
+        self._check(self._lib.mxd_sha256_batch(self._ctx, spans, n, out), "mxd_sha256_batch")
         raw = bytes(out)
         return [raw[32 * i:32 * i + 32] for i in range(n)]
 
     def sha256_file(self, path: str) -> Tuple[bytes, int]:
         out = (C.c_uint8 * 32)()
         size = C.c_uint64()
-        N.check(self._lib.mxd_sha256_file(self._ctx, path.encode(), out, C.byref(size)), "mxd_sha256_file")
+        self._check(self._lib.mxd_sha256_file(self._ctx, path.encode(), out, C.byref(size)), "mxd_sha256_file")
         return bytes(out), size.value
 
     def sha256_files(self, paths: Sequence[str]) -> Tuple[List[bytes], List[int]]:
@@ -181,9 +214,55 @@ class Engine:
         arr = (C.c_char_p * max(n, 1))(*[p.encode() for p in paths])
         out = (C.c_uint8 * (32 * max(n, 1)))()
         sizes = (C.c_uint64 * max(n, 1))()
-        N.check(self._lib.mxd_sha256_files(self._ctx, arr, n, out, sizes), "mxd_sha256_files")
+        self._check(self._lib.mxd_sha256_files(self._ctx, arr, n, out, sizes), "mxd_sha256_files")
         raw = bytes(out)
         return [raw[32 * i:32 * i + 32] for i in range(n)], [int(sizes[i]) for i in range(n)]
+
+    def sha256_file_jobs(self, jobs: Sequence[dict]) -> List[dict]:
+        """The general per-file form (mxd_sha256_file_jobs).  Each job: {"path": str, "ranges": [(off, len)...] or
+        None, "sink": callable(offset, bytes) or None}.  Returns per job {"status", "size", "digests": [bytes]};
+        never raises for a per-file failure."""
+        n = len(jobs)
+        arr = (N.FileJob * max(n, 1))()
+        keep = []
+        for i, jb in enumerate(jobs):
+            rng = jb.get("ranges") or []
+            parts = (N.Part * max(len(rng), 1))()
+            for k, (off, ln) in enumerate(rng):
+                parts[k].offset, parts[k].length = off, ln
+            out = (C.c_uint8 * (32 * max(len(rng), 1)))()
+            path = jb["path"].encode()
+            cb = None
+            if jb.get("sink"):
+                sink = jb["sink"]
+
+                def _cb(user, offset, data, nbytes, sink=sink):
+                    try:
+                        sink(offset, C.string_at(data, nbytes))
+                        return 0
+                    except Exception:
+                        return 1
+                cb = N.SINK_FN(_cb)
+            arr[i].path = path
+            arr[i].ranges = parts if rng else None
+            arr[i].nranges = len(rng)
+            arr[i].out = C.cast(out, C.POINTER(C.c_uint8))
+            arr[i].sink = C.cast(cb, C.c_void_p) if cb else None
+            keep.append((parts, out, path, cb))
+        self._lib.mxd_sha256_file_jobs(self._ctx, arr, n)
+        res = []
+        for i in range(n):
+            raw = bytes(keep[i][1])
+            res.append({"status": arr[i].status, "size": arr[i].size,
+                        "digests": [raw[32 * k:32 * k + 32] for k in range(len(raw) // 32)]})
+        return res
+
+    def sha256_file_ranges(self, path: str, ranges: Sequence[Tuple[int, int]], sink=None):
+        """SHA-256 of each (offset, length) range of one file in ONE pass, optionally teeing every byte to
+        ``sink(offset, data)``.  -> (digests, size)"""
+        r = self.sha256_file_jobs([{"path": path, "ranges": list(ranges), "sink": sink}])[0]
+        self._check(r["status"], "mxd_sha256_file_jobs")
+        return r["digests"][:len(ranges)], r["size"]
 
     def sha256_file_parts(self, path: str, parts: Sequence[Tuple[int, int]]) -> List[bytes]:
         """SHA-256 of each (offset, length) range of a file, e.g. the ranges calc_parts() yields."""
@@ -192,7 +271,7 @@ class Engine:
         for i, (off, ln) in enumerate(parts):
             arr[i].offset, arr[i].length = off, ln
         out = (C.c_uint8 * (32 * max(n, 1)))()
-        N.check(self._lib.mxd_sha256_file_parts(self._ctx, path.encode(), arr, n, out), "mxd_sha256_file_parts")
+        self._check(self._lib.mxd_sha256_file_parts(self._ctx, path.encode(), arr, n, out), "mxd_sha256_file_parts")
         raw = bytes(out)
         return [raw[32 * i:32 * i + 32] for i in range(n)]
 
@@ -205,7 +284,7 @@ class Engine:
             spans[i].len = ln
         w = (C.c_uint8 * (32 * max(n, 1))).from_buffer_copy(b"".join(want) + b"\0" * (32 * max(n, 1) - 32 * n))
         ok = (C.c_uint8 * max(n, 1))()
-        N.check(self._lib.mxd_verify_batch(self._ctx, spans, w, n, ok), "mxd_verify_batch")
+        self._check(self._lib.mxd_verify_batch(self._ctx, spans, w, n, ok), "mxd_verify_batch")
         return [bool(ok[i]) for i in range(n)]
 
     def verify_files(self, paths: Sequence[str], want: Sequence[bytes]) -> List[bool]:
@@ -213,7 +292,7 @@ class Engine:
         arr = (C.c_char_p * max(n, 1))(*[p.encode() for p in paths])
         w = (C.c_uint8 * (32 * max(n, 1))).from_buffer_copy(b"".join(want) + b"\0" * (32 * max(n, 1) - 32 * n))
         ok = (C.c_uint8 * max(n, 1))()
-        N.check(self._lib.mxd_verify_files(self._ctx, arr, w, n, ok), "mxd_verify_files")
+        self._check(self._lib.mxd_verify_files(self._ctx, arr, w, n, ok), "mxd_verify_files")
         return [bool(ok[i]) for i in range(n)]
 
     # -- incremental hasher ------------------------------------------------------------------
@@ -232,7 +311,7 @@ class Engine:
         chunks = (C.c_uint8 * (32 * nch))()
         got = C.c_uint64()
         root = (C.c_uint8 * 32)()
-        N.check(self._lib.mxd_tree_digest(self._ctx, ptr, n, _tp(chunk, leaf, fanout), chunks, C.byref(got), root),
+        self._check(self._lib.mxd_tree_digest(self._ctx, ptr, n, _tp(chunk, leaf, fanout), chunks, C.byref(got), root),
                 "mxd_tree_digest")
         raw = bytes(chunks)
         return [raw[32 * i:32 * i + 32] for i in range(got.value)], bytes(root)
@@ -246,7 +325,7 @@ class Engine:
         got = C.c_uint64()
         sz = C.c_uint64()
         root = (C.c_uint8 * 32)()
-        N.check(self._lib.mxd_tree_digest_file(self._ctx, path.encode(), _tp(chunk, leaf, fanout), chunks, nch,
+        self._check(self._lib.mxd_tree_digest_file(self._ctx, path.encode(), _tp(chunk, leaf, fanout), chunks, nch,
                                                C.byref(got), C.byref(sz), root), "mxd_tree_digest_file")
         raw = bytes(chunks)
         return [raw[32 * i:32 * i + 32] for i in range(got.value)], bytes(root), sz.value
@@ -269,7 +348,7 @@ class Engine:
             except Exception:
                 return 1
         cb = N.SINK_FN(_cb)
-        N.check(self._lib.mxd_tree_digest_file_tee(self._ctx, path.encode(), _tp(chunk, leaf, fanout), chunks, nch,
+        self._check(self._lib.mxd_tree_digest_file_tee(self._ctx, path.encode(), _tp(chunk, leaf, fanout), chunks, nch,
                                                    C.byref(got), C.byref(sz), root, C.cast(cb, C.c_void_p), None),
                 "mxd_tree_digest_file_tee")
         raw = bytes(chunks)
@@ -279,7 +358,7 @@ class Engine:
                         fanout: int = DEFAULT_FANOUT) -> bytes:
         nch = max(1, -(-n // chunk))
         chunks = (C.c_uint8 * (32 * nch))()
-        N.check(self._lib.mxd_tree_chunks(self._ctx, ptr, n, _tp(chunk, leaf, fanout), chunks), "mxd_tree_chunks")
+        self._check(self._lib.mxd_tree_chunks(self._ctx, ptr, n, _tp(chunk, leaf, fanout), chunks), "mxd_tree_chunks")
         return bytes(chunks)
 
     def tree_chunks(self, data, chunk: int = DEFAULT_CHUNK, leaf: int = DEFAULT_LEAF, fanout: int = DEFAULT_FANOUT) -> bytes:
@@ -291,36 +370,36 @@ class Engine:
         n = len(chunk_digests) // 32
         arr = (C.c_uint8 * len(chunk_digests)).from_buffer_copy(chunk_digests)
         root = (C.c_uint8 * 32)()
-        N.check(self._lib.mxd_tree_finish(self._ctx, arr, n, size, _tp(chunk, leaf, fanout), root), "mxd_tree_finish")
+        self._check(self._lib.mxd_tree_finish(self._ctx, arr, n, size, _tp(chunk, leaf, fanout), root), "mxd_tree_finish")
         return bytes(root)
 
     # -- device-resident asynchronous forms (raw device pointers, cudaStream_t as int) -----------
     def dev_sha256_segments(self, dev: int, d_data: int, nbytes: int, seg: int, d_out: int, stream: int = 0):
-        N.check(self._lib.mxd_dev_sha256_segments(self._ctx, dev, d_data, nbytes, seg, d_out, stream), "mxd_dev_sha256_segments")
+        self._check(self._lib.mxd_dev_sha256_segments(self._ctx, dev, d_data, nbytes, seg, d_out, stream), "mxd_dev_sha256_segments")
 
     def dev_sha256_batch(self, dev: int, d_spans: int, n: int, d_out: int, stream: int = 0):
-        N.check(self._lib.mxd_dev_sha256_batch(self._ctx, dev, d_spans, n, d_out, stream), "mxd_dev_sha256_batch")
+        self._check(self._lib.mxd_dev_sha256_batch(self._ctx, dev, d_spans, n, d_out, stream), "mxd_dev_sha256_batch")
 
     def dev_tree_chunks(self, dev: int, d_piece: int, nbytes: int, tp: Tuple[int, int, int], d_chunks: int, stream: int = 0):
         """tp = (chunk, leaf, fanout)"""
-        N.check(self._lib.mxd_dev_tree_chunks(self._ctx, dev, d_piece, nbytes, _tp(*tp), d_chunks, stream), "mxd_dev_tree_chunks")
+        self._check(self._lib.mxd_dev_tree_chunks(self._ctx, dev, d_piece, nbytes, _tp(*tp), d_chunks, stream), "mxd_dev_tree_chunks")
 
     def dev_tree_finish(self, dev: int, d_chunks: int, nchunks: int, size: int, tp: Tuple[int, int, int], d_root: int, stream: int = 0):
-        N.check(self._lib.mxd_dev_tree_finish(self._ctx, dev, d_chunks, nchunks, size, _tp(*tp), d_root, stream), "mxd_dev_tree_finish")
+        self._check(self._lib.mxd_dev_tree_finish(self._ctx, dev, d_chunks, nchunks, size, _tp(*tp), d_root, stream), "mxd_dev_tree_finish")
 
     def dev_tree_digest(self, dev: int, d_data: int, size: int, tp: Tuple[int, int, int], d_chunks: int, d_root: int, stream: int = 0):
-        N.check(self._lib.mxd_dev_tree_digest(self._ctx, dev, d_data, size, _tp(*tp), d_chunks, d_root, stream), "mxd_dev_tree_digest")
+        self._check(self._lib.mxd_dev_tree_digest(self._ctx, dev, d_data, size, _tp(*tp), d_chunks, d_root, stream), "mxd_dev_tree_digest")
 
     def dev_compare(self, dev: int, d_got: int, d_want: int, n: int, d_ok: int, stream: int = 0):
-        N.check(self._lib.mxd_dev_compare(self._ctx, dev, d_got, d_want, n, d_ok, stream), "mxd_dev_compare")
+        self._check(self._lib.mxd_dev_compare(self._ctx, dev, d_got, d_want, n, d_ok, stream), "mxd_dev_compare")
 
     def dev_gen_fill(self, dev: int, d_dst: int, offset: int, n: int, seed: int, stream: int = 0):
-        N.check(self._lib.mxd_dev_gen_fill(self._ctx, dev, d_dst, offset, n, seed, stream), "mxd_dev_gen_fill")
+        self._check(self._lib.mxd_dev_gen_fill(self._ctx, dev, d_dst, offset, n, seed, stream), "mxd_dev_gen_fill")
 
     # -- pinned memory -----------------------------------------------------------------------
     def host_alloc(self, nbytes: int) -> int:
         p = C.c_void_p()
-        N.check(self._lib.mxd_host_alloc(self._ctx, C.byref(p), nbytes), "mxd_host_alloc")
+        self._check(self._lib.mxd_host_alloc(self._ctx, C.byref(p), nbytes), "mxd_host_alloc")
         return p.value
 
     def host_free(self, ptr: int):
@@ -333,27 +412,34 @@ class Hasher:
     def __init__(self, engine: Engine):
         self._e = engine
         self._h = C.c_void_p()
-        N.check(engine._lib.mxd_hasher_new(engine._ctx, C.byref(self._h)), "mxd_hasher_new")
+        engine._check(engine._lib.mxd_hasher_new(engine._ctx, C.byref(self._h)), "mxd_hasher_new")
 
     def write(self, data) -> int:
         addr, n, keep = _buf(data)
-        N.check(self._e._lib.mxd_hasher_write(self._h, addr, n), "mxd_hasher_write")
+        self._e._check(self._e._lib.mxd_hasher_write(self._h, addr, n), "mxd_hasher_write")
         return n
 
     update = write
 
     def sum(self) -> bytes:
         out = (C.c_uint8 * 32)()
-        N.check(self._e._lib.mxd_hasher_sum(self._h, out), "mxd_hasher_sum")
+        self._e._check(self._e._lib.mxd_hasher_sum(self._h, out), "mxd_hasher_sum")
         return bytes(out)
 
     digest = sum
 
     def reset(self):
-        N.check(self._e._lib.mxd_hasher_reset(self._h), "mxd_hasher_reset")
+        self._e._check(self._e._lib.mxd_hasher_reset(self._h), "mxd_hasher_reset")
 
     def size(self) -> int:
+        """hash.Hash.Size(): 32"""
         return int(self._e._lib.mxd_hasher_size(self._h))
+
+    def block_size(self) -> int:
+        return int(self._e._lib.mxd_hasher_block_size(self._h))
+
+    def written(self) -> int:
+        return int(self._e._lib.mxd_hasher_written(self._h))
 
     def close(self):
         if self._h:

@@ -24,7 +24,7 @@ def test_header_and_library_agree():
     for name in names:
         assert hasattr(lib, name), f"{name} declared in include/modelx_digest.h but not exported"
         assert name in N.PROTOTYPES, f"{name} has no ctypes prototype"
-    assert lib.mxd_abi_version() == 1
+    assert lib.mxd_abi_version() == 2
 
 
 def test_split_matches_oracle(oracle):

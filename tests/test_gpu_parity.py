@@ -105,9 +105,9 @@ def test_hasher_incremental(engine):
         total += n
         assert h.sum() == ref.digest()       # Sum must not disturb the running state
         assert h.sum() == ref.digest()
-        assert h.size() == total
+        assert h.written() == total and h.size() == 32 and h.block_size() == 64
     h.reset()
-    assert h.sum() == hashlib.sha256(b"").digest() and h.size() == 0
+    assert h.sum() == hashlib.sha256(b"").digest() and h.written() == 0
     h.write(b"abc")
     assert h.sum().hex() == KAT[1][1]
     h.close()
@@ -298,14 +298,26 @@ def test_concurrent_callers(engine, oracle):
 
 
 def test_cancel(oracle):
+    """An operation handle is one Go context (push.go:150-159): canceling it fails the calls made through it -- also
+    calls that start afterwards -- and nobody else's; a root-level cancel only aborts what is in flight."""
     blob = oracle.gen(0, 20_000_000, SEED)
+    want = oracle.tree_digest(blob, 1 << 20, 16 << 10, 8)[2]
     with modelx_b200.Engine(devices=[0], ring_bytes=4 << 20) as eng:
-        eng.cancel()
-        with pytest.raises(modelx_b200.MxdError) as ei:
-            eng.tree_digest(blob, 1 << 20, 16 << 10, 8)
-        assert ei.value.status == -6
-        eng.reset_cancel()
-        assert eng.tree_digest(blob, 1 << 20, 16 << 10, 8)[1] == oracle.tree_digest(blob, 1 << 20, 16 << 10, 8)[2]
+        with eng.op() as op, eng.op() as other:
+            op.cancel()
+            assert op.is_canceled() and not other.is_canceled()
+            with pytest.raises(modelx_b200.MxdError) as ei:
+                op.tree_digest(blob, 1 << 20, 16 << 10, 8)
+            assert ei.value.status == -6
+            with pytest.raises(modelx_b200.MxdError) as ei:
+                op.sha256(blob[:1000])
+            assert ei.value.status == -6
+            assert other.tree_digest(blob, 1 << 20, 16 << 10, 8)[1] == want       # a sibling operation is untouched
+            assert eng.sha256(blob[:1000]) == hashlib.sha256(blob[:1000]).digest()  # and so is the root handle
+            op.reset_cancel()
+            assert op.tree_digest(blob, 1 << 20, 16 << 10, 8)[1] == want
+        eng.cancel()                                                               # nothing in flight: a no-op, not sticky
+        assert eng.tree_digest(blob, 1 << 20, 16 << 10, 8)[1] == want
 
 
 # ------------------------------------------------------------------------------------------------
