@@ -11,6 +11,8 @@
 #include "kernels.h"
 #include "sha256_device.cuh"
 #include <cstdlib>
+#include <cstdio>
+#include <vector>
 
 namespace mxd {
 
@@ -421,10 +423,13 @@ __device__ __forceinline__ void store_digest(uint8_t* out, const uint32_t (&h)[8
 constexpr uint32_t kMaxSmid = 1024;
 constexpr uint32_t kSchedHeaderWords = 4 + 2 * kMaxSmid;
 
+template <bool FUSED>
 __global__ void __launch_bounds__(kThreads, 12) k_tree_leaves(const LeafJob j, const uint32_t n_units, const uint32_t nsm,
-                                                              const uint32_t kper, const uint32_t mode) {
-    __shared__ uint32_t dig[2][64][8];
+                                                              const uint32_t kper, const uint32_t mode, unsigned long long* dbg) {
+    __shared__ uint32_t dig[FUSED ? 2 : 1][FUSED ? 64 : 1][8];
     __shared__ uint32_t s_info[4];
+    unsigned long long t_begin = 0;
+    if (dbg != nullptr && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
     const uint32_t tid = threadIdx.x;
     const uint32_t one = j.one;
     uint32_t* const n_seen = j.sched;
@@ -492,10 +497,9 @@ __global__ void __launch_bounds__(kThreads, 12) k_tree_leaves(const LeafJob j, c
         uint32_t h[8];
         sha256_iv(h);
         absorb(ptr, nfull, r, nblk, len << 3, live, h, one);
-        if (j.fused == 0) {
+        if constexpr (!FUSED) {
             if (live) store_digest(j.out + 32 * leaf_idx, h);
-            continue;
-        }
+        } else {
         // ---- the tree levels that fit inside these 64 leaves, through shared memory -----------------------
 #pragma unroll
         for (int k = 0; k < 8; ++k) dig[0][tid][k] = h[k];
@@ -524,6 +528,15 @@ __global__ void __launch_bounds__(kThreads, 12) k_tree_leaves(const LeafJob j, c
             store_digest(j.out + 32 * (((uint64_t)u * 64u) / span + tid), g);
         }
         __syncthreads();                            // dig[] is free for the next unit
+        }
+    }
+    if (dbg != nullptr && threadIdx.x == 0) {       // developer aid (MXD_LEAF_DEBUG): where did this CTA run, when, how much
+        unsigned long long t_end; uint32_t smid;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        unsigned long long* r = dbg + 4ull * blockIdx.x;
+        r[0] = ((unsigned long long)smid << 32) | (mode == 0 ? s_info[0] : 0xffffu);
+        r[1] = t_begin; r[2] = t_end; r[3] = count;
     }
 }
 
@@ -646,7 +659,7 @@ static void leaf_geometry(int* nsm, int* per_sm) {
     if (cache_sm[dev] == 0) {
         int sms = 0, occ = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_tree_leaves, kThreads, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_tree_leaves<false>, kThreads, 0);
         cache_occ[dev] = occ > 0 ? occ : 1;
         cache_sm[dev] = sms > 0 ? sms : 1;
     }
@@ -654,7 +667,12 @@ static void leaf_geometry(int* nsm, int* per_sm) {
 }
 
 uint32_t leaf_fusable_levels(uint32_t fanout, uint32_t want) {
-    if (getenv("MXD_TUNE_NOFUSE")) return 0;
+    // In-kernel tree levels are OFF by default: a level-1 pass has 8 live lanes and a level-2 pass 1, but each warp
+    // instruction still holds the 16-lane ALU pipe for 2 clk, so the 10 extra block compressions per 64 leaves cost
+    // 1.95 % of the pipe against 0.28 % for the same nodes in wide launches (measured: 101.9 vs 98.96 ms on 100 GB,
+    // profiles/r02_leaf_variants.txt).  MXD_TUNE_FUSE=1 enables them for A/B.
+    static const bool on = [] { const char* e = getenv("MXD_TUNE_FUSE"); return e && atoi(e) > 0; }();
+    if (!on) return 0;
     uint32_t lv = 0;
     uint64_t span = 1;
     while (lv < want && span * fanout <= 64 && 64 % (span * fanout) == 0) { span *= fanout; ++lv; }
@@ -663,26 +681,52 @@ uint32_t leaf_fusable_levels(uint32_t fanout, uint32_t want) {
 
 uint64_t leaf_sched_bytes(uint64_t n0) { return (kSchedHeaderWords + (n0 + 63) / 64) * sizeof(uint32_t); }
 
-cudaError_t launch_tree_leaves(const LeafJob& job, cudaStream_t stream) {
+template <bool FUSED>
+static cudaError_t launch_leaves_impl(const LeafJob& job, cudaStream_t stream) {
     const uint64_t units64 = (job.n0 + 63) / 64;
     if (units64 == 0 || units64 > 0x7fffffffull || job.sched == nullptr) return cudaErrorInvalidValue;
     const uint32_t n_units = (uint32_t)units64;
     int nsm = 1, per_sm = 1;
     leaf_geometry(&nsm, &per_sm);
     static const int tune = [] { const char* e = getenv("MXD_TUNE_LEAF_SCHED"); return e ? atoi(e) : 0; }();   // 1: always grid-scheduled
+    static const int kper_env = [] { const char* e = getenv("MXD_TUNE_LEAF_KPER"); return e ? atoi(e) : 0; }();  // CTAs per SM (A/B)
+    if (kper_env > 0 && kper_env < per_sm) per_sm = kper_env;
     const uint32_t resident = (uint32_t)nsm * (uint32_t)per_sm;
     if (tune == 1 || n_units < 2 * resident || (uint32_t)nsm > kMaxSmid) {
         // small input (or A/B): plain grid, one unit per CTA (mode 1 with grid == units)
-        k_tree_leaves<<<n_units, kThreads, 0, stream>>>(job, n_units, (uint32_t)nsm, (uint32_t)per_sm, 1u);
+        k_tree_leaves<FUSED><<<n_units, kThreads, 0, stream>>>(job, n_units, (uint32_t)nsm, (uint32_t)per_sm, 1u, nullptr);
         return cudaGetLastError();
     }
+    static const char* dbg_path = getenv("MXD_LEAF_DEBUG");
+    unsigned long long* dbg = nullptr;
+    if (dbg_path) cudaMalloc(&dbg, 32ull * resident);
     cudaError_t e = cudaMemsetAsync(job.sched, 0, leaf_sched_bytes(job.n0), stream);
     if (e != cudaSuccess) return e;
-    k_tree_leaves<<<resident, kThreads, 0, stream>>>(job, n_units, (uint32_t)nsm, (uint32_t)per_sm, 0u);
+    k_tree_leaves<FUSED><<<resident, kThreads, 0, stream>>>(job, n_units, (uint32_t)nsm, (uint32_t)per_sm, 0u, dbg);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     // sweep: hashes whatever unit is still unclaimed (none when every SM received its per_sm CTAs)
-    k_tree_leaves<<<(unsigned)nsm, kThreads, 0, stream>>>(job, n_units, (uint32_t)nsm, (uint32_t)per_sm, 2u);
-    return cudaGetLastError();
+    k_tree_leaves<FUSED><<<(unsigned)nsm, kThreads, 0, stream>>>(job, n_units, (uint32_t)nsm, (uint32_t)per_sm, 2u, nullptr);
+    e = cudaGetLastError();
+    if (dbg) {      // developer aid: per-SM placement and timing of the persistent launch, appended to $MXD_LEAF_DEBUG
+        cudaStreamSynchronize(stream);
+        std::vector<unsigned long long> h(4ull * resident);
+        cudaMemcpy(h.data(), dbg, 32ull * resident, cudaMemcpyDeviceToHost);
+        cudaFree(dbg);
+        if (FILE* f = fopen(dbg_path, "a")) {
+            unsigned long long t0 = ~0ull, t1 = 0;
+            for (uint32_t i = 0; i < resident; ++i) { if (h[4 * i + 1] && h[4 * i + 1] < t0) t0 = h[4 * i + 1]; if (h[4 * i + 2] > t1) t1 = h[4 * i + 2]; }
+            fprintf(f, "launch units=%u nsm=%d per_sm=%d span_us=%.1f\n", n_units, nsm, per_sm, (t1 - t0) / 1e3);
+            for (uint32_t i = 0; i < resident; ++i)
+                fprintf(f, "cta %u smid %llu slot %llu start_us %.1f end_us %.1f units %llu\n", i, h[4 * i] >> 32, h[4 * i] & 0xffffffffull,
+                        (h[4 * i + 1] - t0) / 1e3, (h[4 * i + 2] - t0) / 1e3, h[4 * i + 3]);
+            fclose(f);
+        }
+    }
+    return e;
+}
+
+cudaError_t launch_tree_leaves(const LeafJob& job, cudaStream_t stream) {
+    return job.fused ? launch_leaves_impl<true>(job, stream) : launch_leaves_impl<false>(job, stream);
 }
 
 // scratch layout: two buffers of ceil(n/fanout)*32 bytes for the wide levels, then 16 KiB for k_tree_top's own

@@ -26,3 +26,26 @@ def engine():
     eng = modelx_b200.Engine(devices=[0])
     yield eng
     eng.close()
+
+
+@pytest.fixture(scope="session")
+def mock_lib():
+    """Path of the CPU test double of libmodelxdigest.so (host sources + a synchronous CUDA stand-in + oracle
+    hashing, see tests/mock/include/cuda_runtime.h).  Test infrastructure: never loaded by the product."""
+    from tests import mock_build
+    return mock_build.build()
+
+
+@pytest.fixture(params=[pytest.param("mock"), pytest.param("cuda", marks=pytest.mark.gpu)])
+def backend(request, mock_lib):
+    """Host-logic tests run twice: against the test double here (`-m "not gpu"`) and against the CUDA build on the
+    B200 (`-m gpu`).  Yields the lib_path argument for modelx_b200.Engine (None = the product library)."""
+    return mock_lib if request.param == "mock" else None
+
+
+@pytest.fixture
+def any_engine(backend):
+    import modelx_b200
+    eng = modelx_b200.Engine(devices=[0], lib_path=backend)
+    yield eng
+    eng.close()
