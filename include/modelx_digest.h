@@ -183,6 +183,10 @@ int mxd_tree_digest_file_tee(mxd_ctx*, const char* path, const mxd_tree_params* 
 /* Sharded form (one process per GPU): chunk digests of a piece that starts on a chunk boundary... */
 int mxd_tree_chunks(mxd_ctx*, const void* piece /*host or device*/, uint64_t nbytes, const mxd_tree_params* tp,
                     uint8_t* chunk_digests /*max(1, ceil(nbytes/chunk))*32*/);
+/* The same for a piece of a FILE: bytes [offset, offset+nbytes) of `path`, offset a multiple of the chunk size.  What a
+ * rank of a sharded push calls for its chunk range; streams through the pinned ring like mxd_tree_digest_file. */
+int mxd_tree_chunks_file(mxd_ctx*, const char* path, uint64_t offset, uint64_t nbytes, const mxd_tree_params* tp,
+                         uint8_t* chunk_digests /*max(1, ceil(nbytes/chunk))*32*/);
 /* ...and the levels above the gathered chunk list (the only step after the all-gather). */
 int mxd_tree_finish(mxd_ctx*, const uint8_t* chunk_digests, uint64_t nchunks, uint64_t size,
                     const mxd_tree_params* tp, uint8_t root[32]);

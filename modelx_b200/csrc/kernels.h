@@ -78,5 +78,7 @@ cudaError_t launch_compare(const uint8_t* got, const uint8_t* want, uint64_t n, 
 // bytes [offset, offset+n) of the splitmix64 counter stream (offset and n multiples of 8, dst 8-byte aligned)
 cudaError_t launch_gen_fill(void* dst, uint64_t offset, uint64_t n, uint64_t seed, cudaStream_t stream);
 int sha256_kernel_regs();
+// kernels this library has launched in this process (every <<<>>> of sha256_kernels.cu counts one)
+uint64_t kernel_launch_count();
 
 }  // namespace mxd

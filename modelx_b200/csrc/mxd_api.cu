@@ -688,7 +688,7 @@ int mxd_get_stats(const mxd_ctx* h, mxd_stats* out) {
     if (!handle_ok(h) || !out) return fail(MXD_ERR_INVALID, "mxd_get_stats: null");
     const Core* c = h->core;
     memset(out, 0, sizeof *out);
-    out->kernel_launches = c->launches.load(); out->bytes_hashed = c->bytes_hashed.load();
+    out->kernel_launches = mxd::kernel_launch_count(); out->bytes_hashed = c->bytes_hashed.load();
     out->h2d_bytes = c->h2d.load(); out->d2h_bytes = c->d2h.load();
     out->src_bytes_read = c->src_read.load();
     out->open_files = (uint64_t)std::max(0, c->open_fds.load());
@@ -927,6 +927,23 @@ int mxd_tree_digest_file_tee(mxd_ctx* h, const char* path, const mxd_tree_params
     close(fd);
     if (rc != MXD_OK) return rc;
     return host_tree_finish(h->core, h->core->devs[0], t, chunks, nchunks, size, root);
+}
+
+int mxd_tree_chunks_file(mxd_ctx* h, const char* path, uint64_t offset, uint64_t nbytes, const mxd_tree_params* tp, uint8_t* out) {
+    Tree t;
+    if (!handle_ok(h) || !path || !tree_resolve(tp, &t) || !out) return fail(MXD_ERR_INVALID, "tree_chunks_file: bad arguments");
+    if (offset % t.chunk) return fail(MXD_ERR_INVALID, "tree_chunks_file: the piece must start on a chunk boundary");
+    const CancelScope cs(h);
+    if (cs.canceled()) return fail(MXD_ERR_CANCELED, "canceled");
+    int fd = open(path, O_RDONLY | O_CLOEXEC);
+    if (fd < 0) return fail(MXD_ERR_IO, std::string("open ") + path + ": " + strerror(errno));
+    struct stat st;
+    if (fstat(fd, &st) != 0) { int e = errno; close(fd); errno = e; return fail(MXD_ERR_IO, std::string("fstat: ") + strerror(e)); }
+    if (offset > (uint64_t)st.st_size || nbytes > (uint64_t)st.st_size - offset) { close(fd); return fail(MXD_ERR_IO, "tree_chunks_file: the piece lies outside the file"); }
+    Source src; src.fd = fd; src.base = offset;
+    int rc = host_tree_chunks_all(h->core, cs, t, src, nbytes, out);
+    close(fd);
+    return rc;
 }
 
 // ---- whole-message digests ---------------------------------------------------------------------------

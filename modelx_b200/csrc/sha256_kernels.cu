@@ -10,6 +10,7 @@
 // of shared memory.
 #include "kernels.h"
 #include "sha256_device.cuh"
+#include <atomic>
 #include <cstdlib>
 #include <cstdio>
 #include <vector>
@@ -613,6 +614,9 @@ __global__ void k_gen_fill(uint64_t* __restrict__ dst, uint64_t first_word, uint
 // Occupancy: 24 warps per SM at 80 registers is the default (16..24 warps measure the same, 1.01 TB/s); 32 warps
 // at 63 registers is 11 % slower (profiles/r01_quick_bench_v3.txt).  MXD_TUNE_MINB=8 keeps the 32-warp build
 // selectable for A/B profiling.
+static std::atomic<uint64_t> g_launches{0};
+uint64_t kernel_launch_count() { return g_launches.load(); }
+
 static int g_minb = [] { const char* e = getenv("MXD_TUNE_MINB"); const int v = e ? atoi(e) : 6; return (v == 8 || v == 4) ? v : 6; }();
 
 static long g_coop_max = [] { const char* e = getenv("MXD_TUNE_COOP"); return e ? atol(e) : 32768L; }();
@@ -625,17 +629,19 @@ cudaError_t launch_sha256(const MsgJob& job, cudaStream_t stream) {
     // is between 16k chains (coop 675 vs 610 GB/s) and 64k (791 vs 834).  MXD_TUNE_COOP=0 disables, =N sets the threshold.
     if (job.nmsg <= (uint64_t)g_coop_max) {
         const uint64_t cblocks = (job.nmsg + 31) / 32;
+        ++g_launches;
         k_sha256_chains_coop<<<(unsigned)cblocks, 64, 0, stream>>>(job);
         return cudaGetLastError();
     }
-    if (g_minb == 8)      k_sha256_lanes<16><<<(unsigned)blocks, kThreads, 0, stream>>>(job);
-    else if (g_minb == 4) k_sha256_lanes<8><<<(unsigned)blocks, kThreads, 0, stream>>>(job);
-    else                  k_sha256_lanes<12><<<(unsigned)blocks, kThreads, 0, stream>>>(job);
+    if (g_minb == 8)      { ++g_launches; k_sha256_lanes<16><<<(unsigned)blocks, kThreads, 0, stream>>>(job); }
+    else if (g_minb == 4) { ++g_launches; k_sha256_lanes<8><<<(unsigned)blocks, kThreads, 0, stream>>>(job); }
+    else                  { ++g_launches; k_sha256_lanes<12><<<(unsigned)blocks, kThreads, 0, stream>>>(job); }
     return cudaGetLastError();
 }
 
 cudaError_t launch_compare(const uint8_t* got, const uint8_t* want, uint64_t n, uint8_t* ok, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
+    ++g_launches;
     k_compare<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(got, want, n, ok);
     return cudaGetLastError();
 }
@@ -646,6 +652,7 @@ cudaError_t launch_gen_fill(void* dst, uint64_t offset, uint64_t n, uint64_t see
     const uint64_t nwords = n >> 3;
     uint64_t blocks = (nwords + 255) / 256;
     if (blocks > 148ull * 64) blocks = 148ull * 64;
+    ++g_launches;
     k_gen_fill<<<(unsigned)blocks, 256, 0, stream>>>(static_cast<uint64_t*>(dst), offset >> 3, nwords, seed);
     return cudaGetLastError();
 }
@@ -694,6 +701,7 @@ static cudaError_t launch_leaves_impl(const LeafJob& job, cudaStream_t stream) {
     const uint32_t resident = (uint32_t)nsm * (uint32_t)per_sm;
     if (tune == 1 || n_units < 2 * resident || (uint32_t)nsm > kMaxSmid) {
         // small input (or A/B): plain grid, one unit per CTA (mode 1 with grid == units)
+        ++g_launches;
         k_tree_leaves<FUSED><<<n_units, kThreads, 0, stream>>>(job, n_units, (uint32_t)nsm, (uint32_t)per_sm, 1u, nullptr);
         return cudaGetLastError();
     }
@@ -702,9 +710,11 @@ static cudaError_t launch_leaves_impl(const LeafJob& job, cudaStream_t stream) {
     if (dbg_path) cudaMalloc(&dbg, 32ull * resident);
     cudaError_t e = cudaMemsetAsync(job.sched, 0, leaf_sched_bytes(job.n0), stream);
     if (e != cudaSuccess) return e;
+    ++g_launches;
     k_tree_leaves<FUSED><<<resident, kThreads, 0, stream>>>(job, n_units, (uint32_t)nsm, (uint32_t)per_sm, 0u, dbg);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     // sweep: hashes whatever unit is still unclaimed (none when every SM received its per_sm CTAs)
+    ++g_launches;
     k_tree_leaves<FUSED><<<(unsigned)nsm, kThreads, 0, stream>>>(job, n_units, (uint32_t)nsm, (uint32_t)per_sm, 2u, nullptr);
     e = cudaGetLastError();
     if (dbg) {      // developer aid: per-SM placement and timing of the persistent launch, appended to $MXD_LEAF_DEBUG
@@ -749,6 +759,7 @@ cudaError_t launch_tree_top(const uint8_t* digests, uint64_t n, uint32_t fanout,
         if (e != cudaSuccess) return e;
         cur = j.out; which ^= 1; n = j.nmsg;
     }
+    ++g_launches;
     k_tree_top<<<1, 256, 0, stream>>>(cur, n, fanout, size, leaf, scratch + 2 * half, root, 1u);
     return cudaGetLastError();
 }

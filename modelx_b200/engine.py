@@ -361,6 +361,15 @@ class Engine:
         self._check(self._lib.mxd_tree_chunks(self._ctx, ptr, n, _tp(chunk, leaf, fanout), chunks), "mxd_tree_chunks")
         return bytes(chunks)
 
+    def tree_chunks_file(self, path: str, offset: int, nbytes: int, chunk: int = DEFAULT_CHUNK, leaf: int = DEFAULT_LEAF,
+                         fanout: int = DEFAULT_FANOUT) -> bytes:
+        """Chunk digests of bytes [offset, offset+nbytes) of a file (offset on a chunk boundary): a rank's share."""
+        nch = max(1, -(-nbytes // chunk))
+        chunks = (C.c_uint8 * (32 * nch))()
+        self._check(self._lib.mxd_tree_chunks_file(self._ctx, path.encode(), offset, nbytes, _tp(chunk, leaf, fanout), chunks),
+                    "mxd_tree_chunks_file")
+        return bytes(chunks)
+
     def tree_chunks(self, data, chunk: int = DEFAULT_CHUNK, leaf: int = DEFAULT_LEAF, fanout: int = DEFAULT_FANOUT) -> bytes:
         addr, n, keep = _buf(data)
         return self.tree_chunks_ptr(addr, n, chunk, leaf, fanout)

@@ -130,9 +130,7 @@ typedef struct {
 static void* seg_worker(void* arg) {
     seg_job* j = (seg_job*)arg;
     for (;;) {
-        pthread_mutex_lock(&j->mu);
-        uint64_t lo = j->next; j->next += j->grain;
-        pthread_mutex_unlock(&j->mu);
+        uint64_t lo = __atomic_fetch_add(&j->next, j->grain, __ATOMIC_RELAXED);
         if (lo >= j->nseg) break;
         uint64_t hi = lo + j->grain; if (hi > j->nseg) hi = j->nseg;
         for (uint64_t i = lo; i < hi; ++i) {

@@ -6,6 +6,7 @@
 #include "../../modelx_b200/csrc/kernels.h"
 #include "../../oracle/oracle.h"
 
+#include <atomic>
 #include <cstdio>
 #include <vector>
 
@@ -63,8 +64,12 @@ void chain(uint32_t h[8], const uint8_t* p, uint64_t len, uint64_t prefix, bool 
 }
 }  // namespace
 
+static std::atomic<uint64_t> g_launches{0};
+uint64_t kernel_launch_count() { return g_launches.load(); }
+
 cudaError_t launch_sha256(const MsgJob& j, cudaStream_t) {
     if (j.one != 1) return cudaErrorInvalidValue;
+    ++g_launches;
     for (uint64_t m = 0; m < j.nmsg; ++m) {
         const uint8_t* ptr; uint64_t len, prefix = j.prefix_all; uint64_t sidx = m, oidx = m; bool fin = j.finalize != 0, live = true, load = false;
         if (j.descs) {

@@ -21,6 +21,7 @@ def test_reference_arm_prints_one_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["vs_baseline"] is None and "workload" in d["config"]
+    assert d["native_so_loaded"] is False          # the reference arm must not map the product library
 
 
 def test_reference_arm_is_silent_on_other_ranks():
