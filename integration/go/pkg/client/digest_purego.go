@@ -6,20 +6,11 @@ package client
 
 import (
 	"context"
-	"os"
 
 	"github.com/opencontainers/go-digest"
 )
 
-func digestFile(ctx context.Context, path string) (digest.Digest, error) {
-	f, err := os.Open(path)
-	if err != nil {
-		return "", err
-	}
-	defer f.Close()
-	go func() {
-		<-ctx.Done()
-		f.Close()
-	}()
-	return digest.FromReader(f)
-}
+func digestFile(ctx context.Context, path string) (digest.Digest, error) { return digestFileGo(ctx, path) }
+
+// prefetchDigests is a no-op without the GPU engine: the 3 goroutines hash as they always did.
+func prefetchDigests(ctx context.Context, paths []string) (context.Context, error) { return ctx, nil }

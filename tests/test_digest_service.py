@@ -173,3 +173,18 @@ def test_routing_advice():
     assert modelx_b200.batch_pays_off(1000, 128 * 10 ** 9, 128 * 10 ** 6)       # config 5 (1000 x 128 MB)
     assert modelx_b200.batch_pays_off(256, 256 * 64 * 10 ** 6, 64 * 10 ** 6)
     assert not modelx_b200.batch_pays_off(0, 0, 0)
+
+
+def test_c_program_cancels_one_of_three(backend, tmp_path):
+    """the same contract from plain C through dlopen -- what the cgo shim binds."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "cancel_one_of_three"
+    subprocess.run(["gcc", "-O1", "-o", str(exe), os.path.join(root, "tests", "c", "cancel_one_of_three.c"), "-ldl", "-lpthread"], check=True)
+    paths, want = _files(tmp_path, [30_000_000, 30_000_000, 30_000_000], seed=9)
+    lib = backend or modelx_b200.LIB_PATH
+    args = [str(exe), lib]
+    for p, w in zip(paths, want):
+        args += [p, w.hex()]
+    out = subprocess.run(args, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip().endswith("PASS"), out.stdout + out.stderr
