@@ -64,8 +64,8 @@ typedef struct {
  *   MXD_MAX_OPEN_FILES  files the whole-message digest service may hold open at once (default RLIMIT_NOFILE/2 - 32, capped at 4096)
  *   MXD_TUNE_COOP       largest launch (in messages) that uses the two-warp cooperative kernel (default 32768, 0 = never)
  *   MXD_TUNE_MINB=8     select the 63-register build of the lanes kernel (A/B profiling only)
- *   MXD_TUNE_LEAF=legacy        tree leaves through the generic kernel, every tree level its own launch (A/B profiling only)
- *   MXD_TUNE_LEAF_SCHED=1       fused leaf kernel with a plain grid instead of the per-SM round schedule (A/B profiling only) */
+ *   MXD_TUNE_LEAF_SCHED=2       leaf kernel as a persistent grid with a static per-SM round schedule (measured slower; A/B only)
+ *   MXD_TUNE_FUSE=1             first tree levels inside the leaf kernel (measured slower: 8-lane warps hold the ALU pipe; A/B only) */
 
 /* ---- lifecycle ------------------------------------------------------------------------- */
 /* devices/ndev: CUDA ordinals to drive from this process (ndev == 0: all visible devices).

@@ -65,6 +65,9 @@ cudaError_t launch_sha256(const MsgJob& job, cudaStream_t stream);
 // state; a launch may not overlap another launch using the same scratch.
 cudaError_t launch_tree_leaves(const LeafJob& job, cudaStream_t stream);
 uint64_t leaf_sched_bytes(uint64_t n0);
+// true when an A/B knob (MXD_TUNE_FUSE=1, MXD_TUNE_LEAF_SCHED=2) selects k_tree_leaves; by default tree leaves go through
+// launch_sha256 like every other level (both experiments measured slower, see sha256_kernels.cu)
+bool leaf_kernel_selected();
 // How many tree levels launch_tree_leaves will fuse for this fanout when asked for at most `want` levels.
 uint32_t leaf_fusable_levels(uint32_t fanout, uint32_t want);
 // All levels above a digest list (n >= 1 digests of 32 bytes, groups of `fanout`) and the root message, one launch:

@@ -255,10 +255,9 @@ int enqueue_level(Core* c, const uint8_t* d_in, uint64_t n, uint64_t fanout, uin
 }
 
 // How many tree levels the leaf kernel computes itself for this tree when a piece is at least `avail` bytes long
-// (0 = legacy path: plain leaf digests, every level its own launch; MXD_TUNE_LEAF=legacy forces that).
+// (0 = plain leaf digests, every level up to the chunk list its own launch: the default).
 uint32_t fused_levels(const Tree& t, uint64_t avail) {
-    static const bool legacy = [] { const char* e = getenv("MXD_TUNE_LEAF"); return e && !strcmp(e, "legacy"); }();
-    if (legacy) return 0;
+    if (!mxd::leaf_kernel_selected()) return 0;
     uint32_t f = mxd::leaf_fusable_levels((uint32_t)t.fanout, (uint32_t)t.klevel);
     while (f > 0 && t.leaf * ipow(t.fanout, f) > avail) --f;
     return f;
@@ -267,8 +266,9 @@ uint32_t fused_levels(const Tree& t, uint64_t avail) {
 // blob bytes in device memory -> digests of tree level `fused` (one launch, leaves never touch DRAM when fused > 0)
 int enqueue_leaves(Core* c, const Tree& t, uint32_t fused, const uint8_t* d_piece, uint64_t nbytes, uint8_t* d_out, cudaStream_t st) {
     const uint64_t n0 = nbytes ? (nbytes + t.leaf - 1) / t.leaf : 1;
-    static const bool legacy = [] { const char* e = getenv("MXD_TUNE_LEAF"); return e && !strcmp(e, "legacy"); }();
-    if (legacy) return enqueue_segments(c, d_piece, nbytes, t.leaf, d_out, st, /*leaf_level=*/true);
+    // default: the leaf level is an ordinary segment launch (k_sha256_lanes, or the two-warp chain kernel for the few
+    // thousand leaves of one ring slot); k_tree_leaves only when an A/B knob asks for it
+    if (!mxd::leaf_kernel_selected()) return enqueue_segments(c, d_piece, nbytes, t.leaf, d_out, st, /*leaf_level=*/true);
     ProfScope prof(c, nbytes, st);
     uint32_t* sched = nullptr;
     MXD_CUDA(cudaMallocAsync(&sched, mxd::leaf_sched_bytes(n0), st));

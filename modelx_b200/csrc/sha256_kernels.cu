@@ -410,7 +410,9 @@ __device__ __forceinline__ void store_digest(uint8_t* out, const uint32_t (&h)[8
 // one digest per MiB leaves the kernel instead of 64), so levels 1..fused cost no launch, no DRAM round trip and no
 // dependency tail behind the leaf launch.
 //
-// Scheduling (mode 0, large inputs): a grid-scheduled launch ends with a drain in which the CTAs of an SM finish at
+// Scheduling.  Default (mode 1): one unit per CTA, the hardware block scheduler refills slots as CTAs finish.
+// Mode 0 (MXD_TUNE_LEAF_SCHED=2, kept for the record -- measured slower, see launch_leaves_impl) tries to remove the
+// drain at the end of a launch: a grid-scheduled launch ends with a drain in which the CTAs of an SM finish at
 // scattered times and the last leaves run on a nearly empty machine (measured: a constant ~0.33 ms per launch,
 // 2.6 % of a 12.5 GB launch).  Here the grid is exactly one CTA per resident slot (SMs x 12).  Every CTA looks up
 // the SM it landed on (%smid) and takes a slot number there; SM s owns a contiguous share of the units, and its
@@ -686,6 +688,14 @@ uint32_t leaf_fusable_levels(uint32_t fanout, uint32_t want) {
     return lv;
 }
 
+bool leaf_kernel_selected() {
+    static const bool on = [] {
+        const char* f = getenv("MXD_TUNE_FUSE"); const char* s = getenv("MXD_TUNE_LEAF_SCHED");
+        return (f && atoi(f) > 0) || (s && atoi(s) == 2);
+    }();
+    return on;
+}
+
 uint64_t leaf_sched_bytes(uint64_t n0) { return (kSchedHeaderWords + (n0 + 63) / 64) * sizeof(uint32_t); }
 
 template <bool FUSED>
@@ -695,11 +705,15 @@ static cudaError_t launch_leaves_impl(const LeafJob& job, cudaStream_t stream) {
     const uint32_t n_units = (uint32_t)units64;
     int nsm = 1, per_sm = 1;
     leaf_geometry(&nsm, &per_sm);
-    static const int tune = [] { const char* e = getenv("MXD_TUNE_LEAF_SCHED"); return e ? atoi(e) : 0; }();   // 1: always grid-scheduled
+    // 2: the persistent per-SM round schedule (mode 0 of k_tree_leaves); default: the hardware block scheduler.
+    // Measured (profiles/r02_leaf_variants.txt, r02_leaf_persistent_debug.txt): placement is exactly 12 CTAs on every
+    // SM, yet equal-work CTAs of one SM finish anywhere between 3.3 and 13.5 ms -- the warp scheduler is greedy, not
+    // fair -- so static shares end in a long low-occupancy tail (13.67 vs 12.72 ms on 12.5 GB).  Dynamic refill wins.
+    static const int tune = [] { const char* e = getenv("MXD_TUNE_LEAF_SCHED"); return e ? atoi(e) : 1; }();
     static const int kper_env = [] { const char* e = getenv("MXD_TUNE_LEAF_KPER"); return e ? atoi(e) : 0; }();  // CTAs per SM (A/B)
     if (kper_env > 0 && kper_env < per_sm) per_sm = kper_env;
     const uint32_t resident = (uint32_t)nsm * (uint32_t)per_sm;
-    if (tune == 1 || n_units < 2 * resident || (uint32_t)nsm > kMaxSmid) {
+    if (tune != 2 || n_units < 2 * resident || (uint32_t)nsm > kMaxSmid) {
         // small input (or A/B): plain grid, one unit per CTA (mode 1 with grid == units)
         ++g_launches;
         k_tree_leaves<FUSED><<<n_units, kThreads, 0, stream>>>(job, n_units, (uint32_t)nsm, (uint32_t)per_sm, 1u, nullptr);

@@ -99,6 +99,7 @@ uint32_t leaf_fusable_levels(uint32_t fanout, uint32_t want) {
     return lv;
 }
 uint64_t leaf_sched_bytes(uint64_t n0) { return 64 + (n0 + 63) / 64 * 4; }
+bool leaf_kernel_selected() { const char* f = getenv("MXD_TUNE_FUSE"); return f && atoi(f) > 0; }
 
 cudaError_t launch_tree_leaves(const LeafJob& j, cudaStream_t st) {
     std::vector<uint8_t> cur(j.n0 * 32);
