@@ -676,6 +676,19 @@ def run_compat(args, eng, torch, dist, dev, world, rank, run_tag, barrier, max_o
                           "still read, copied to the GPU and hashed",
               "gpu": {"value": nb * bb / dt / GB, "unit": "GB/s", "ms": dt * 1e3, "files_per_rank": len(mine),
                       "api": "mxd_verify_files (one coalesced batch per rank)"}}
+        # the same 1000 paths verified by their chunked identity (tree-keyed blobs, `modelx.digest` annotation): a file is a
+        # whole tree of independent leaves, so this is PCIe/host bound instead of chain-latency bound, and it scales with GPUs
+        want_roots = eng.tree_digest_files(base_files)[0] if base_files else []
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            roots, _sz, st = eng.tree_digest_files(paths) if paths else ([], [], [])
+        dtt = max_over_ranks((time.perf_counter() - t0) / reps)
+        if any(st) or any(r != want_roots[j % distinct] for j, r in enumerate(roots)):
+            raise SystemExit("compat config 5: tree-keyed verify mismatch")
+        c5["gpu_tree_identity"] = {"value": nb * bb / dtt / GB, "unit": "GB/s", "ms": dtt * 1e3,
+                                   "api": "mxd_tree_digest_files (all files of a rank in one pipelined pass; what mxc_pull_check runs for "
+                                          "tree-keyed descriptors)"}
         if rank == 0 and paths:
             sample = paths[:24]
             tcpu, res = cpu_ref3(orc, sample)

@@ -180,6 +180,11 @@ int mxd_tree_digest_file(mxd_ctx*, const char* path, const mxd_tree_params* tp,
 int mxd_tree_digest_file_tee(mxd_ctx*, const char* path, const mxd_tree_params* tp, uint8_t* chunk_digests,
                              uint64_t cap_chunks, uint64_t* nchunks, uint64_t* size, uint8_t root[32],
                              mxd_sink_fn sink, void* user);
+/* Tree roots of MANY files in one pipelined pass (e.g. the pull-side check of a manifest whose blobs are tree keyed): the
+ * files stream through the ring back to back, so the copy engine and the SMs do not drain between files.  roots: n*32;
+ * sizes and status (per file, MXD_OK or that file's I/O error) may be NULL.  Returns MXD_OK or the first failing status. */
+int mxd_tree_digest_files(mxd_ctx*, const char* const* paths, uint64_t n, const mxd_tree_params* tp, uint8_t* roots,
+                          uint64_t* sizes, int* status);
 /* Sharded form (one process per GPU): chunk digests of a piece that starts on a chunk boundary... */
 int mxd_tree_chunks(mxd_ctx*, const void* piece /*host or device*/, uint64_t nbytes, const mxd_tree_params* tp,
                     uint8_t* chunk_digests /*max(1, ceil(nbytes/chunk))*32*/);

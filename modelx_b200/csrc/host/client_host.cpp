@@ -1117,8 +1117,8 @@ struct FsUploader {
 // (mxc_push_local_tree) are checked with the tree digest instead; directories by re-archiving them (TGZ(dir, "")).
 struct PullState { std::string name, digest, state; };
 int pull_check(mxd_ctx* ctx, const std::string& basedir, const std::vector<Descriptor>& descs, std::vector<PullState>* out) {
-    std::vector<size_t> present;
-    std::vector<std::string> paths;
+    std::vector<size_t> present, tree_present;
+    std::vector<std::string> paths, tree_paths;
     for (size_t i = 0; i < descs.size(); ++i) {
         const Descriptor& d = descs[i];
         out->push_back({d.name, d.digest, "missing"});
@@ -1138,14 +1138,16 @@ int pull_check(mxd_ctx* ctx, const std::string& basedir, const std::vector<Descr
         if (!have) continue;
         // os.Open succeeds on a directory and digest.FromReader then fails with EISDIR (pull.go:116-119)
         if (S_ISDIR(st.st_mode)) return fail(MXD_ERR_IO, "read " + p + ": is a directory");
-        if (is_tree_keyed(d)) {
-            uint8_t root[32]; uint64_t nch = 0, sz = 0;
-            int rc = mxd_tree_digest_file(ctx, p.c_str(), nullptr, nullptr, 0, &nch, &sz, root);
-            if (rc != MXD_OK) return fail(rc, std::string("tree digest: ") + mxd_last_error());
-            (*out)[i].state = (digest_str(root) == d.digest) ? "already exists" : "differs";
-        } else {
-            present.push_back(i); paths.push_back(p);
-        }
+        if (is_tree_keyed(d)) { tree_present.push_back(i); tree_paths.push_back(p); }
+        else { present.push_back(i); paths.push_back(p); }
+    }
+    if (!tree_present.empty()) {       // tree-keyed blobs: one pipelined pass over all of them
+        std::vector<const char*> cp; for (auto& p : tree_paths) cp.push_back(p.c_str());
+        std::vector<uint8_t> roots(32 * tree_present.size());
+        int rc = mxd_tree_digest_files(ctx, cp.data(), cp.size(), nullptr, roots.data(), nullptr, nullptr);
+        if (rc != MXD_OK) return fail(rc, std::string("tree digest: ") + mxd_last_error());
+        for (size_t k = 0; k < tree_present.size(); ++k)
+            (*out)[tree_present[k]].state = (digest_str(&roots[32 * k]) == descs[tree_present[k]].digest) ? "already exists" : "differs";
     }
     if (!present.empty()) {
         std::vector<mxd_file_job> jobs(present.size());

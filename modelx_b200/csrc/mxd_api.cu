@@ -345,14 +345,19 @@ struct TraceSlot {
 // Stream [0, nbytes) of `src` through device `d`'s ring and hash it as tree leaves of t.leaf bytes (with `fused`
 // levels computed in the same kernel) into d_out.  H2D copies run on the copy stream, kernels on the compute
 // stream; a slot is refilled only after the kernel that read it has finished, so copy k+1.. overlap kernel k.
+struct RingCursor { uint64_t i = 0; };     // running slot index: lets consecutive blobs share one pipelined pass over the ring
+
 int stream_leaves(Core* c, const CancelScope& cs, DevState* d, const Tree& t, uint32_t fused, const Source& src, uint64_t nbytes,
-                  uint8_t* d_out) {
+                  uint8_t* d_out, RingCursor* cur = nullptr) {
+    RingCursor own;
+    if (!cur) cur = &own;
     const uint64_t unit = t.leaf * ipow(t.fanout, fused);       // bytes under one output digest
     const uint64_t per_slot = (d->slot_bytes / unit) * unit;
     if (per_slot == 0) return fail(MXD_ERR_INVALID, "ring slot smaller than one leaf; raise ring_bytes");
     if (nbytes == 0) return enqueue_leaves(c, t, fused, nullptr, 0, d_out, d->compute);
     uint64_t off = 0;
-    for (uint64_t i = 0; off < nbytes; ++i) {
+    for (; off < nbytes; ++cur->i) {
+        const uint64_t i = cur->i;
         if (cs.canceled()) return fail(MXD_ERR_CANCELED, "canceled");
         const int s = (int)(i % kSlots);
         const uint64_t n = (nbytes - off < per_slot) ? nbytes - off : per_slot;
@@ -447,6 +452,58 @@ int host_tree_chunks_all(Core* c, const CancelScope& cs, const Tree& t, const So
     for (int g = 0; g < G; ++g)
         if (rcs[g] != MXD_OK) return fail(rcs[g], errs[g]);
     return MXD_OK;
+}
+
+// Tree roots of many files on one device, back to back through the ring: the copy engine and the SMs never drain between
+// files (a per-file call pays pipeline fill and a sync per file: 128 MB files would run at less than half the rate).
+// Everything of a file after its last slot (levels, root, D2H of the root) is stream-ordered behind it; one sync at the end.
+struct TreeFileItem { const char* path; uint8_t* root; uint64_t size = 0; int status = MXD_OK; std::string error; };
+
+int tree_files_on_device(Core* c, const CancelScope& cs, DevState* d, const Tree& t, std::vector<TreeFileItem*>& items) {
+    std::lock_guard<std::mutex> lk(d->mu);
+    DeviceGuard guard(d->ordinal);
+    uint8_t* h_roots = nullptr;
+    MXD_CUDA(cudaHostAlloc(&h_roots, 32 * std::max<size_t>(items.size(), 1), cudaHostAllocPortable));
+    RingCursor cur;
+    int rc = MXD_OK;
+    const uint32_t fused = fused_levels(t, d->slot_bytes);
+    const uint64_t span = ipow(t.fanout, fused);
+    for (size_t k = 0; k < items.size() && rc == MXD_OK; ++k) {
+        TreeFileItem& it = *items[k];
+        int fd = open(it.path, O_RDONLY | O_CLOEXEC);
+        struct stat st;
+        if (fd < 0 || fstat(fd, &st) != 0 || S_ISDIR(st.st_mode)) {
+            it.status = MXD_ERR_IO; it.error = std::string(fd < 0 ? "open " : "read ") + it.path + ": " + (fd >= 0 && S_ISDIR(st.st_mode) ? "is a directory" : strerror(errno));
+            if (fd >= 0) close(fd);
+            continue;
+        }
+        it.size = (uint64_t)st.st_size;
+        const uint64_t n0 = it.size ? (it.size + t.leaf - 1) / t.leaf : 1, nf = (n0 + span - 1) / span;
+        const uint64_t nchunks = it.size ? (it.size + t.chunk - 1) / t.chunk : 1;
+        uint8_t *d_lvl = nullptr, *d_chunks = nullptr;      // [level digests][chunk digests][root]
+        cudaError_t e = cudaMallocAsync(&d_lvl, nf * 32, d->compute);
+        if (e == cudaSuccess) e = cudaMallocAsync(&d_chunks, nchunks * 32 + 32, d->compute);
+        if (e != cudaSuccess) { close(fd); rc = fail(MXD_ERR_CUDA, std::string("cudaMallocAsync: ") + cudaGetErrorString(e)); break; }
+        Source src; src.fd = fd;
+        int r = stream_leaves(c, cs, d, t, fused, src, it.size, d_lvl, &cur);
+        close(fd);
+        if (r == MXD_OK) {
+            if ((int)fused == t.klevel) e = cudaMemcpyAsync(d_chunks, d_lvl, nchunks * 32, cudaMemcpyDeviceToDevice, d->compute);
+            else r = enqueue_levels_to_chunks(c, t, fused, d_lvl, nf, d_chunks, d->compute);
+        }
+        if (r == MXD_OK && e == cudaSuccess) r = enqueue_tree_finish(c, t, d_chunks, nchunks, it.size, d_chunks + nchunks * 32, d->compute);
+        if (r == MXD_OK && e == cudaSuccess) e = cudaMemcpyAsync(h_roots + 32 * k, d_chunks + nchunks * 32, 32, cudaMemcpyDeviceToHost, d->compute);
+        cudaFreeAsync(d_lvl, d->compute); cudaFreeAsync(d_chunks, d->compute);
+        if (r == MXD_ERR_CANCELED || r == MXD_ERR_CUDA || e != cudaSuccess) { rc = (e != cudaSuccess) ? fail(MXD_ERR_CUDA, cudaGetErrorString(e)) : r; break; }
+        if (r != MXD_OK) { it.status = r; it.error = last_error(); }      // I/O trouble with this file only
+        c->d2h += 32;
+    }
+    cudaError_t e = cudaStreamSynchronize(d->compute);
+    cudaStreamSynchronize(d->copy);
+    if (rc == MXD_OK && e != cudaSuccess) rc = fail(MXD_ERR_CUDA, std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e));
+    if (rc == MXD_OK) for (size_t k = 0; k < items.size(); ++k) if (items[k]->status == MXD_OK) memcpy(items[k]->root, h_roots + 32 * k, 32);
+    cudaFreeHost(h_roots);
+    return rc;
 }
 
 // upper levels + root from a host-resident chunk list (tiny: 32 B per chunk)
@@ -598,8 +655,22 @@ int mxd_open(mxd_ctx** out, const int* devices, int ndev, uint64_t ring_bytes) {
     int stage_threads = 0;
     if (const char* env = getenv("MXD_STAGE_THREADS")) stage_threads = atoi(env);
     if (stage_threads <= 0) {
-        const unsigned hw = std::thread::hardware_concurrency();
-        stage_threads = (int)std::min<unsigned>(16, std::max<unsigned>(1, hw / (unsigned)ords.size()));
+        // CPUs this process may really use: affinity mask, capped by a cgroup CPU quota (the bench container has 128
+        // CPUs visible and a quota of 16), shared with the other ranks of a torchrun launch on the same node
+        unsigned usable = std::thread::hardware_concurrency();
+        cpu_set_t aff;
+        if (sched_getaffinity(0, sizeof aff, &aff) == 0 && CPU_COUNT(&aff) > 0) usable = (unsigned)CPU_COUNT(&aff);
+        if (FILE* f = fopen("/sys/fs/cgroup/cpu.max", "r")) {
+            char q[64] = {0}; unsigned long period = 0;
+            if (fscanf(f, "%63s %lu", q, &period) == 2 && strcmp(q, "max") != 0 && period > 0) {
+                const unsigned long quota = strtoul(q, nullptr, 10) / period;
+                if (quota > 0 && quota < usable) usable = (unsigned)quota;
+            }
+            fclose(f);
+        }
+        unsigned sharers = (unsigned)ords.size();
+        if (const char* lw = getenv("LOCAL_WORLD_SIZE")) { const int v = atoi(lw); if (v > 0) sharers = std::max<unsigned>(sharers, (unsigned)v * (unsigned)ords.size()); }
+        stage_threads = (int)std::min<unsigned>(16, std::max<unsigned>(2, usable / std::max(1u, sharers)));
     }
     for (int ord : ords) {
         auto* d = new DevState();
@@ -944,6 +1015,34 @@ int mxd_tree_chunks_file(mxd_ctx* h, const char* path, uint64_t offset, uint64_t
     int rc = host_tree_chunks_all(h->core, cs, t, src, nbytes, out);
     close(fd);
     return rc;
+}
+
+int mxd_tree_digest_files(mxd_ctx* h, const char* const* paths, uint64_t n, const mxd_tree_params* tp, uint8_t* roots,
+                          uint64_t* sizes, int* status) {
+    Tree t;
+    if (!handle_ok(h) || !tree_resolve(tp, &t) || (n && (!paths || !roots))) return fail(MXD_ERR_INVALID, "tree_digest_files: bad arguments");
+    if (n == 0) return MXD_OK;
+    Core* c = h->core;
+    const CancelScope cs(h);
+    if (cs.canceled()) return fail(MXD_ERR_CANCELED, "canceled");
+    std::vector<TreeFileItem> items(n);
+    for (uint64_t i = 0; i < n; ++i) { if (!paths[i]) return fail(MXD_ERR_INVALID, "tree_digest_files: null path"); items[i].path = paths[i]; items[i].root = roots + 32 * i; }
+    // files dealt round-robin over the context's devices, one thread per device
+    const size_t G = std::min<size_t>(c->devs.size(), n);
+    std::vector<std::vector<TreeFileItem*>> share(G);
+    for (uint64_t i = 0; i < n; ++i) share[i % G].push_back(&items[i]);
+    std::vector<int> rcs(G, MXD_OK); std::vector<std::string> errs(G);
+    auto work = [&](size_t g) { rcs[g] = tree_files_on_device(c, cs, c->devs[g], t, share[g]); if (rcs[g] != MXD_OK) errs[g] = last_error(); };
+    if (G == 1) work(0);
+    else { std::vector<std::thread> th; for (size_t g = 0; g < G; ++g) th.emplace_back(work, g); for (auto& x : th) x.join(); }
+    for (size_t g = 0; g < G; ++g) if (rcs[g] != MXD_OK) return fail(rcs[g], errs[g]);
+    int first = MXD_OK; std::string first_err;
+    for (uint64_t i = 0; i < n; ++i) {
+        if (sizes) sizes[i] = items[i].size;
+        if (status) status[i] = items[i].status;
+        if (items[i].status != MXD_OK && first == MXD_OK) { first = items[i].status; first_err = items[i].error; }
+    }
+    return first == MXD_OK ? MXD_OK : fail(first, first_err);
 }
 
 // ---- whole-message digests ---------------------------------------------------------------------------

@@ -361,6 +361,20 @@ class Engine:
         self._check(self._lib.mxd_tree_chunks(self._ctx, ptr, n, _tp(chunk, leaf, fanout), chunks), "mxd_tree_chunks")
         return bytes(chunks)
 
+    def tree_digest_files(self, paths: Sequence[str], chunk: int = DEFAULT_CHUNK, leaf: int = DEFAULT_LEAF,
+                          fanout: int = DEFAULT_FANOUT):
+        """Tree roots of many files in one pipelined pass -> (roots, sizes, statuses); per-file failures do not raise."""
+        n = len(paths)
+        arr = (C.c_char_p * max(n, 1))(*[p.encode() for p in paths])
+        roots = (C.c_uint8 * (32 * max(n, 1)))()
+        sizes = (C.c_uint64 * max(n, 1))()
+        status = (C.c_int * max(n, 1))()
+        rc = self._lib.mxd_tree_digest_files(self._ctx, arr, n, _tp(chunk, leaf, fanout), roots, sizes, status)
+        if rc != 0 and all(status[i] == 0 for i in range(n)):
+            self._check(rc, "mxd_tree_digest_files")
+        raw = bytes(roots)
+        return [raw[32 * i:32 * i + 32] for i in range(n)], [int(sizes[i]) for i in range(n)], [int(status[i]) for i in range(n)]
+
     def tree_chunks_file(self, path: str, offset: int, nbytes: int, chunk: int = DEFAULT_CHUNK, leaf: int = DEFAULT_LEAF,
                          fanout: int = DEFAULT_FANOUT) -> bytes:
         """Chunk digests of bytes [offset, offset+nbytes) of a file (offset on a chunk boundary): a rank's share."""
