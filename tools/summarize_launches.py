@@ -22,11 +22,11 @@ total = sum(v[1] for v in tot.values())
 print(f"# {len(seq)} launches, {total:.3f} ms of kernel time (ncu: cold-cache, serialised; compare shares, not absolutes)")
 for n, (c, ms) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
     print(f"{ms:12.3f} ms {100*ms/total:6.2f}%  x{c:<5d} {n}")
-# one step of the HBM-resident digest = the run of launches from one big leaf launch to k_tree_root
+# one step of the HBM-resident digest = the run of launches from one big leaf launch to k_tree_top
 big = [i for i, (n, g, ms) in enumerate(seq) if "k_sha256_lanes" in n and ms > 5.0]
 if big:
     i = big[0]
-    j = next(k for k in range(i, len(seq)) if "k_tree_root" in seq[k][0])
+    j = next(k for k in range(i, len(seq)) if ("k_tree_top" in seq[k][0] or "k_tree_root" in seq[k][0]))
     step = seq[i:j + 1]
     st = sum(ms for _, _, ms in step)
     print(f"\n# one step (launches {i}..{j}): {st:.3f} ms")
