@@ -26,7 +26,7 @@ typedef void* cudaMemPool_t;
 enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3, cudaMemcpyDefault = 4 };
 enum cudaMemoryType { cudaMemoryTypeUnregistered = 0, cudaMemoryTypeHost = 1, cudaMemoryTypeDevice = 2, cudaMemoryTypeManaged = 3 };
 struct cudaPointerAttributes { cudaMemoryType type; int device; void* devicePointer; void* hostPointer; };
-enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaHostAllocPortable = 1, cudaHostRegisterPortable = 1 };
+enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaHostAllocPortable = 1, cudaHostRegisterPortable = 1, cudaHostRegisterReadOnly = 8 };
 enum cudaMemPoolAttr { cudaMemPoolAttrReleaseThreshold = 4 };
 
 namespace mockcuda {
