@@ -234,7 +234,10 @@ void WindowFeeder::run() {
             lk.unlock();
             const uint64_t len = std::min(win_, nbytes_ - pick * win_);
             cudaError_t e = cudaHostRegister(const_cast<uint8_t*>(base_ + pick * win_), len, flags_);
-            if (e != cudaSuccess) cudaGetLastError();
+            if (e != cudaSuccess) {
+                if (getenv("MXD_DEBUG_TIMING")) fprintf(stderr, "[mxd] cudaHostRegister(window %zu, %llu bytes, flags %#x): %s -> staged\n", pick, (unsigned long long)len, flags_, cudaGetErrorString(e));
+                cudaGetLastError();
+            }
             lk.lock();
             state_[pick] = e == cudaSuccess ? kReady : kFailed;
             if (e == cudaSuccess) npinned_++;
@@ -267,14 +270,15 @@ void WindowFeeder::retire(uint64_t k, cudaStream_t stream) {
 
 namespace {
 
-// Policy of the zero-copy feed.  MXD_HOST_FEED = stage | map | auto (default): auto pins sources of at least MXD_MAP_MIN
-// bytes (default 1 GiB; smaller ones are cheaper to stage: pinning costs ~0.3 ms + 50 us/MiB).
+// Policy of the zero-copy feed.  MXD_HOST_FEED = stage (default) | map | auto: auto pins sources of at least MXD_MAP_MIN
+// bytes (default 1 GiB; smaller ones are cheaper to stage: pinning costs ~0.3 ms + 50 us/MiB).  OFF by default: measured
+// no faster than staging (profiles/r02_feed_bench.txt), see DESIGN.md section 4.2.
 // MXD_MAP_WINDOW (default 1 GiB), MXD_MAP_THREADS (2), MXD_MAP_DEPTH (windows pinned ahead, 3).
 struct FeedPolicy { int mode; uint64_t min_bytes, window; int threads, depth; };
 const FeedPolicy& feed_policy() {
     static const FeedPolicy p = [] {
-        FeedPolicy q{2, 1ull << 30, 1ull << 30, 2, 3};
-        if (const char* e = getenv("MXD_HOST_FEED")) q.mode = !strcmp(e, "stage") ? 0 : (!strcmp(e, "map") ? 1 : 2);
+        FeedPolicy q{0, 1ull << 30, 1ull << 30, 2, 3};
+        if (const char* e = getenv("MXD_HOST_FEED")) q.mode = !strcmp(e, "map") ? 1 : (!strcmp(e, "auto") ? 2 : 0);
         if (const char* e = getenv("MXD_MAP_MIN")) { uint64_t v = strtoull(e, nullptr, 10); if (v) q.min_bytes = v; }
         if (const char* e = getenv("MXD_MAP_WINDOW")) { uint64_t v = strtoull(e, nullptr, 10); if (v >= (1u << 20)) q.window = v; }
         if (const char* e = getenv("MXD_MAP_THREADS")) { int v = atoi(e); if (v > 0) q.threads = v; }
@@ -491,7 +495,7 @@ int stream_leaves(Core* c, const CancelScope& cs, DevState* d, const Tree& t, ui
         int rc = MXD_OK;
         const double f0 = c->trace_on.load() ? now_ms() : 0;
         const bool direct = src.feeder && src.feeder->acquire(off);     // this window of the source is pinned: no staging copy
-        if (direct) { from = src.feeder->base() + off; c->src_read += n; }
+        if (direct) { from = src.feeder->base() + off; c->src_read += n; c->direct += n; }
         else { PhaseTimer pt("  fill slot"); rc = source_stage(c, src, off, n, h_slot, &from, d->pool); }
         if (rc != MXD_OK) return rc;
         TraceSlot tr(c, d->ordinal, s, n, c->trace_on.load() ? now_ms() - f0 : 0);
@@ -893,6 +897,7 @@ int mxd_get_stats(const mxd_ctx* h, mxd_stats* out) {
     out->h2d_bytes = c->h2d.load(); out->d2h_bytes = c->d2h.load();
     out->src_bytes_read = c->src_read.load();
     out->open_files = (uint64_t)std::max(0, c->open_fds.load());
+    out->direct_h2d_bytes = c->direct.load();
     return MXD_OK;
 }
 

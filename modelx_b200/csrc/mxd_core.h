@@ -127,7 +127,7 @@ struct DevState {
 // What mxd_open creates.  The root handle and every operation handle (mxd_op_begin) point at one Core.
 struct Core {
     std::vector<DevState*> devs;
-    std::atomic<uint64_t> launches{0}, bytes_hashed{0}, h2d{0}, d2h{0}, src_read{0};
+    std::atomic<uint64_t> launches{0}, bytes_hashed{0}, h2d{0}, d2h{0}, src_read{0}, direct{0};
     std::atomic<uint64_t> cancel_gen{0};   // bumped by mxd_cancel(root): aborts every call in flight at that moment
     std::atomic<uint32_t> rr{0};           // round-robin device pick for single-device calls
     std::atomic<int> open_fds{0};          // files the digest service holds open right now

@@ -18,10 +18,13 @@ if not os.path.exists(path) or os.path.getsize(path) != size:
             f.write(memoryview(buf[off:min(off + step, size)].cpu().numpy()))
     del buf
 eng.tree_digest_file(path)
+s0 = eng.stats()
 t0 = time.perf_counter(); reps = 3
 for _ in range(reps):
     chunks, root, sz = eng.tree_digest_file(path)
 dt = (time.perf_counter() - t0) / reps
 tag = " ".join(f"{k}={v}" for k, v in sorted(os.environ.items()) if k.startswith("MXD_"))
 cpus = len(os.sched_getaffinity(0))
-print(f"[{tag or 'defaults'}] cpus={cpus} {size/1e9:g} GB  {dt*1e3:8.1f} ms  {size/dt/1e9:6.1f} GB/s  root {modelx_b200.digest_string(root)[:23]}", flush=True)
+s1 = eng.stats()
+direct = (s1["direct_h2d_bytes"] - s0["direct_h2d_bytes"]) / max(1, s1["h2d_bytes"] - s0["h2d_bytes"])
+print(f"[{tag or 'defaults'}] direct={direct:.2f} cpus={cpus} {size/1e9:g} GB  {dt*1e3:8.1f} ms  {size/dt/1e9:6.1f} GB/s  root {modelx_b200.digest_string(root)[:23]}", flush=True)
