@@ -71,7 +71,7 @@ def test_init_writes_the_reference_template(tmp_path, capsys):
     assert (path / "README.md").read_text() == "mine"          # init.go:93-99: README only when absent
 
 
-def test_init_push_pull_list_roundtrip(backend, repos, tmp_path, capsys):
+def test_init_push_pull_list_roundtrip(backend, repos, tmp_path, capsys, monkeypatch):
     """init -> push -> pull against the local store; the version shows up in index.json."""
     model = tmp_path / "llama"
     assert cli.main(["init", str(model)]) == 0
@@ -95,7 +95,7 @@ def test_init_push_pull_list_roundtrip(backend, repos, tmp_path, capsys):
     # default version is "latest" (pkg/client/registry.go:34-36); default target dir is the repository's base name
     assert cli.main(lib + ["push", "local/project/llama", str(model)]) == 0
     assert (store / "project" / "llama" / "manifests" / "latest").exists()
-    os.chdir(tmp_path)
+    monkeypatch.chdir(tmp_path)
     assert cli.main(lib + ["pull", "local/project/llama@v1"]) == 0
     assert "Pulling file://" in capsys.readouterr().out
     assert (tmp_path / "llama" / "model.safetensors").read_bytes() == weights   # pulled over the source dir: "already exists"
