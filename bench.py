@@ -465,7 +465,12 @@ def run_b200(args):
                          "to the GPU's NUMA node), H2D on a copy stream, leaf kernels on a compute stream",
                "api": "mxd_tree_chunks_file(path, rank's byte range) [+ NCCL all-gather of 32 B/chunk] + mxd_tree_finish",
                "overlap": "leaf-kernel device time per step (leaf_kernel_ms_per_step) is hidden behind the copies; slot timeline "
-                          "in profiles/r02_e2e_slot_timeline.txt"}
+                          "in profiles/r02_e2e_slot_timeline.txt",
+               "host_bound": {"usable_cpus": host_cpu_info()["usable_threads"], "ranks_on_this_node": world,
+                              "note": "staging a page-cache file into the pinned ring costs one CPU copy per byte (~3 GB/s per core); "
+                                      "the ranks of a node share the CPUs the container may use (cgroup quota), so beyond "
+                                      "usable_cpus/16 ranks e2e is bound by host cores, not by PCIe or the GPUs -- compare "
+                                      "e2e_pinned_ceiling, which scales with the GPUs"}}
 
     # ---- PCIe ceiling: a sample of the blob in caller-pinned memory (zero-copy H2D, no staging copy) ------------------
     host_ptr = 0

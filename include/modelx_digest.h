@@ -53,8 +53,7 @@ typedef struct {
     uint64_t h2d_bytes, d2h_bytes;
     uint64_t src_bytes_read;    /* bytes read from files / copied out of host buffers into the pinned ring (read-once accounting) */
     uint64_t open_files;        /* files the digest service holds open right now (bounded, see MXD_MAX_OPEN_FILES) */
-    uint64_t direct_h2d_bytes;  /* bytes the copy engine read straight from a pinned window of the source (MXD_HOST_FEED=map) */
-    uint64_t reserved[1];
+    uint64_t reserved[2];
 } mxd_stats;
 
 /* Environment knobs (read once, at mxd_open / first launch):

@@ -41,7 +41,7 @@ SINK_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64)
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("bytes_hashed", C.c_uint64), ("h2d_bytes", C.c_uint64),
                 ("d2h_bytes", C.c_uint64), ("src_bytes_read", C.c_uint64), ("open_files", C.c_uint64),
-                ("direct_h2d_bytes", C.c_uint64), ("reserved", C.c_uint64 * 1)]
+                ("reserved", C.c_uint64 * 2)]
 
 
 class FileJob(C.Structure):

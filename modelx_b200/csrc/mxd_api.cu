@@ -10,7 +10,6 @@
 #include <cstdlib>
 #include <fcntl.h>
 #include <fstream>
-#include <sys/mman.h>
 #include <sys/resource.h>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -189,133 +188,7 @@ int source_stage(Core* c, const Source& s, uint64_t off, uint64_t n, uint8_t* ds
     return MXD_OK;
 }
 
-// ---- WindowFeeder ------------------------------------------------------------------------------------------------
-WindowFeeder::WindowFeeder(const uint8_t* base, uint64_t nbytes, uint64_t window, int threads, int depth, unsigned flags, int ordinal)
-    : base_(base), nbytes_(nbytes), win_(window), depth_(depth), flags_(flags), ordinal_(ordinal) {
-    const uint64_t n = (nbytes + window - 1) / window;
-    state_.assign(n, kPending);
-    done_.assign(n, nullptr);
-    for (int i = 0; i < threads; ++i) threads_.emplace_back([this] { run(); });
-}
-
-WindowFeeder::~WindowFeeder() {
-    { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
-    cv_.notify_all();
-    for (auto& t : threads_) t.join();
-    DeviceGuard guard(ordinal_);
-    for (size_t k = 0; k < state_.size(); ++k) {
-        if (done_[k]) { cudaEventSynchronize(done_[k]); cudaEventDestroy(done_[k]); }
-        if (state_[k] == kReady || state_[k] == kRetiring) cudaHostUnregister(const_cast<uint8_t*>(base_ + k * win_));
-    }
-}
-
-void WindowFeeder::run() {
-    cudaSetDevice(ordinal_);
-    std::unique_lock<std::mutex> lk(mu_);
-    for (;;) {
-        if (stop_) return;
-        // 1. unpin windows whose copies have completed (keeps the amount of pinned memory bounded)
-        bool did = false;
-        for (size_t k = 0; k < state_.size() && !did; ++k) {
-            if (state_[k] != kRetiring || cudaEventQuery(done_[k]) != cudaSuccess) continue;
-            state_[k] = kBusy;
-            lk.unlock();
-            cudaHostUnregister(const_cast<uint8_t*>(base_ + k * win_));
-            lk.lock();
-            state_[k] = kGone; npinned_--; did = true;
-        }
-        if (did) { cv_.notify_all(); continue; }
-        cudaGetLastError();      // cudaEventQuery's cudaErrorNotReady is not an error
-        // 2. pin the next pending window within `depth` of the consumer
-        size_t pick = state_.size();
-        for (size_t k = consumer_; k < state_.size() && k < consumer_ + (uint64_t)depth_; ++k) if (state_[k] == kPending) { pick = k; break; }
-        if (pick < state_.size() && npinned_.load() < (uint64_t)depth_ + 1) {
-            state_[pick] = kBusy;
-            lk.unlock();
-            const uint64_t len = std::min(win_, nbytes_ - pick * win_);
-            cudaError_t e = cudaHostRegister(const_cast<uint8_t*>(base_ + pick * win_), len, flags_);
-            if (e != cudaSuccess) {
-                if (getenv("MXD_DEBUG_TIMING")) fprintf(stderr, "[mxd] cudaHostRegister(window %zu, %llu bytes, flags %#x): %s -> staged\n", pick, (unsigned long long)len, flags_, cudaGetErrorString(e));
-                cudaGetLastError();
-            }
-            lk.lock();
-            state_[pick] = e == cudaSuccess ? kReady : kFailed;
-            if (e == cudaSuccess) npinned_++;
-            cv_.notify_all();
-            continue;
-        }
-        bool retiring = false;
-        for (int st : state_) retiring |= st == kRetiring;
-        if (retiring) cv_.wait_for(lk, std::chrono::microseconds(200));   // poll the copy-done events
-        else cv_.wait(lk);
-    }
-}
-
-bool WindowFeeder::acquire(uint64_t off) {
-    const uint64_t k = off / win_;
-    std::unique_lock<std::mutex> lk(mu_);
-    if (k > consumer_) { consumer_ = k; cv_.notify_all(); }
-    cv_.wait(lk, [&] { return state_[k] == kReady || state_[k] == kFailed || stop_; });
-    return state_[k] == kReady;
-}
-
-void WindowFeeder::retire(uint64_t k, cudaStream_t stream) {
-    std::lock_guard<std::mutex> lk(mu_);
-    if (k >= state_.size() || state_[k] != kReady) return;
-    if (!done_[k] && cudaEventCreateWithFlags(&done_[k], cudaEventDisableTiming) != cudaSuccess) return;   // stays pinned until ~WindowFeeder
-    cudaEventRecord(done_[k], stream);
-    state_[k] = kRetiring;
-    cv_.notify_all();
-}
-
 namespace {
-
-// Policy of the zero-copy feed.  MXD_HOST_FEED = stage (default) | map | auto: auto pins sources of at least MXD_MAP_MIN
-// bytes (default 1 GiB; smaller ones are cheaper to stage: pinning costs ~0.3 ms + 50 us/MiB).  OFF by default: measured
-// no faster than staging (profiles/r02_feed_bench.txt), see DESIGN.md section 4.2.
-// MXD_MAP_WINDOW (default 1 GiB), MXD_MAP_THREADS (2), MXD_MAP_DEPTH (windows pinned ahead, 3).
-struct FeedPolicy { int mode; uint64_t min_bytes, window; int threads, depth; };
-const FeedPolicy& feed_policy() {
-    static const FeedPolicy p = [] {
-        FeedPolicy q{0, 1ull << 30, 1ull << 30, 2, 3};
-        if (const char* e = getenv("MXD_HOST_FEED")) q.mode = !strcmp(e, "map") ? 1 : (!strcmp(e, "auto") ? 2 : 0);
-        if (const char* e = getenv("MXD_MAP_MIN")) { uint64_t v = strtoull(e, nullptr, 10); if (v) q.min_bytes = v; }
-        if (const char* e = getenv("MXD_MAP_WINDOW")) { uint64_t v = strtoull(e, nullptr, 10); if (v >= (1u << 20)) q.window = v; }
-        if (const char* e = getenv("MXD_MAP_THREADS")) { int v = atoi(e); if (v > 0) q.threads = v; }
-        if (const char* e = getenv("MXD_MAP_DEPTH")) { int v = atoi(e); if (v > 0) q.depth = v; }
-        if (q.mode == 1) q.min_bytes = 1;
-        return q;
-    }();
-    return p;
-}
-
-// Owns the mapping (for files) and the feeder of one streamed piece; empty when the piece is staged the classic way.
-struct ZeroCopy {
-    void* map = nullptr; uint64_t map_len = 0;
-    WindowFeeder* feeder = nullptr;
-    ~ZeroCopy() { delete feeder; if (map) munmap(map, map_len); }
-    // slot_unit: the feeder's window is a multiple of it, so a ring-slot piece never straddles two windows
-    void setup(Source* src, uint64_t nbytes, uint64_t slot_unit, int ordinal) {
-        const FeedPolicy& p = feed_policy();
-        if (p.mode == 0 || nbytes < p.min_bytes || src->pinned || slot_unit == 0) return;
-        const uint8_t* base = nullptr; unsigned flags = cudaHostRegisterPortable;
-        if (src->fd >= 0) {
-            const long page = sysconf(_SC_PAGESIZE);
-            if (page <= 0 || src->base % (uint64_t)page) return;
-            map_len = nbytes;
-            map = mmap(nullptr, map_len, PROT_READ, MAP_SHARED, src->fd, (off_t)src->base);
-            if (map == MAP_FAILED) { map = nullptr; return; }
-            madvise(map, map_len, MADV_SEQUENTIAL);
-            base = static_cast<const uint8_t*>(map);
-            flags |= cudaHostRegisterReadOnly;
-        } else if (src->mem) {
-            base = src->mem;
-        } else return;
-        const uint64_t win = std::max<uint64_t>(slot_unit, p.window / slot_unit * slot_unit);
-        feeder = new WindowFeeder(base, nbytes, win, p.threads, p.depth, flags, ordinal);
-        src->feeder = feeder;
-    }
-};
 
 // Resolved tree parameters: chunk = leaf * fanout^klevel.
 struct Tree {
@@ -494,15 +367,11 @@ int stream_leaves(Core* c, const CancelScope& cs, DevState* d, const Tree& t, ui
         const uint8_t* from = nullptr;
         int rc = MXD_OK;
         const double f0 = c->trace_on.load() ? now_ms() : 0;
-        const bool direct = src.feeder && src.feeder->acquire(off);     // this window of the source is pinned: no staging copy
-        if (direct) { from = src.feeder->base() + off; c->src_read += n; c->direct += n; }
-        else { PhaseTimer pt("  fill slot"); rc = source_stage(c, src, off, n, h_slot, &from, d->pool); }
+        { PhaseTimer pt("  fill slot"); rc = source_stage(c, src, off, n, h_slot, &from, d->pool); }
         if (rc != MXD_OK) return rc;
         TraceSlot tr(c, d->ordinal, s, n, c->trace_on.load() ? now_ms() - f0 : 0);
         if (tr.on) cudaEventRecord(tr.rec.c0, d->copy);
         MXD_CUDA(cudaMemcpyAsync(d_slot, from, n, cudaMemcpyHostToDevice, d->copy));
-        if (direct && (off + n == nbytes || (off + n) / src.feeder->window() != off / src.feeder->window()))
-            src.feeder->retire(off / src.feeder->window(), d->copy);     // last copy out of this window is queued
         if (tr.on) cudaEventRecord(tr.rec.c1, d->copy);
         MXD_CUDA(cudaEventRecord(d->ev_copied[s], d->copy));
         MXD_CUDA(cudaStreamWaitEvent(d->compute, d->ev_copied[s], 0));
@@ -521,13 +390,10 @@ int stream_leaves(Core* c, const CancelScope& cs, DevState* d, const Tree& t, ui
 }
 
 // chunk digests of a host/file piece on one device; result left in device memory d_chunks
-int stream_tree_chunks(Core* c, const CancelScope& cs, DevState* d, const Tree& t, const Source& src_in, uint64_t nbytes, uint8_t* d_chunks) {
+int stream_tree_chunks(Core* c, const CancelScope& cs, DevState* d, const Tree& t, const Source& src, uint64_t nbytes, uint8_t* d_chunks) {
     const uint64_t n0 = nbytes ? (nbytes + t.leaf - 1) / t.leaf : 1;
     const uint32_t fused = fused_levels(t, d->slot_bytes);
     const uint64_t span = ipow(t.fanout, fused);
-    Source src = src_in;
-    ZeroCopy zc;                                   // outlives every copy: stream_tree_chunks syncs before returning
-    zc.setup(&src, nbytes, (d->slot_bytes / (t.leaf * span)) * (t.leaf * span), d->ordinal);
     const uint64_t nf = (n0 + span - 1) / span;
     const bool direct = (int)fused == t.klevel;
     uint8_t* d_lvl = d_chunks;
@@ -897,7 +763,6 @@ int mxd_get_stats(const mxd_ctx* h, mxd_stats* out) {
     out->h2d_bytes = c->h2d.load(); out->d2h_bytes = c->d2h.load();
     out->src_bytes_read = c->src_read.load();
     out->open_files = (uint64_t)std::max(0, c->open_fds.load());
-    out->direct_h2d_bytes = c->direct.load();
     return MXD_OK;
 }
 

@@ -66,8 +66,6 @@ private:
     bool stop_ = false;
 };
 
-class WindowFeeder;
-
 // Where streamed bytes come from: host memory or a byte range of an open file; optionally teed to a sink.
 struct Source {
     const uint8_t* mem = nullptr;
@@ -77,36 +75,6 @@ struct Source {
     mxd_sink_fn sink = nullptr;    // every streamed byte is also handed to this callback, once
     void* sink_user = nullptr;
     uint64_t sink_base = 0;        // logical offset of this source's byte 0 for the sink
-    WindowFeeder* feeder = nullptr; // zero-copy mode: the source is (mapped) host memory pinned window by window
-};
-
-// Zero-copy feed of a large host-resident source (an mmap of a page-cache resident file, or pageable memory): instead of
-// copying every byte into the pinned ring with the CPU (~3 GB/s per core), the source itself is pinned window by window
-// (cudaHostRegister: ~20-37 GB/s on ONE core, profiles/r02_register_probe.txt) a few windows ahead of the copy engine,
-// which then reads the caller's pages directly; windows are unpinned once their copies have completed.  Windows that
-// cannot be pinned fall back to staging.  Registration runs on helper threads so it overlaps the copies.
-class WindowFeeder {
-public:
-    WindowFeeder(const uint8_t* base, uint64_t nbytes, uint64_t window, int threads, int depth, unsigned flags, int ordinal);
-    ~WindowFeeder();
-    const uint8_t* base() const { return base_; }
-    uint64_t window() const { return win_; }
-    // blocks until the window holding byte `off` is pinned (true) or known to be unpinnable (false: stage it)
-    bool acquire(uint64_t off);
-    // every copy out of window k has been enqueued on `stream`: unpin it once they have completed
-    void retire(uint64_t k, cudaStream_t stream);
-    uint64_t pinned_windows() const { return npinned_.load(); }
-private:
-    enum State : int { kPending = 0, kBusy, kReady, kFailed, kRetiring, kGone };
-    void run();
-    const uint8_t* base_; uint64_t nbytes_, win_; int depth_; unsigned flags_; int ordinal_;
-    std::vector<int> state_;
-    std::vector<cudaEvent_t> done_;
-    uint64_t consumer_ = 0;          // highest window the consumer has asked for
-    std::atomic<uint64_t> npinned_{0};
-    bool stop_ = false;
-    std::mutex mu_; std::condition_variable cv_;
-    std::vector<std::thread> threads_;
 };
 
 struct LaneService;
@@ -127,7 +95,7 @@ struct DevState {
 // What mxd_open creates.  The root handle and every operation handle (mxd_op_begin) point at one Core.
 struct Core {
     std::vector<DevState*> devs;
-    std::atomic<uint64_t> launches{0}, bytes_hashed{0}, h2d{0}, d2h{0}, src_read{0}, direct{0};
+    std::atomic<uint64_t> launches{0}, bytes_hashed{0}, h2d{0}, d2h{0}, src_read{0};
     std::atomic<uint64_t> cancel_gen{0};   // bumped by mxd_cancel(root): aborts every call in flight at that moment
     std::atomic<uint32_t> rr{0};           // round-robin device pick for single-device calls
     std::atomic<int> open_fds{0};          // files the digest service holds open right now

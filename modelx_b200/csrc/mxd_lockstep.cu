@@ -167,7 +167,8 @@ struct LaneService {
         if (free_lanes.size() < want_lanes || active.size() >= max_streams) return false;
         if (s->cs.canceled()) { s->status = MXD_ERR_CANCELED; s->error = "canceled"; finish_unadmitted(s); return true; }
         if (rq->path) {
-            if (core->open_fds.fetch_add(1) >= core->fd_cap) { core->open_fds--; return false; }
+            int cur = core->open_fds.load();           // reserve a slot of the open-file budget (never overshoots, even transiently)
+            do { if (cur >= core->fd_cap) return false; } while (!core->open_fds.compare_exchange_weak(cur, cur + 1));
             int fd = open(rq->path, O_RDONLY | O_CLOEXEC);
             struct stat st;
             if (fd < 0 || fstat(fd, &st) != 0) {

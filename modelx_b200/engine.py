@@ -143,7 +143,7 @@ class Engine:
         self._check(self._lib.mxd_get_stats(self._ctx, C.byref(st)), "mxd_get_stats")
         return {"kernel_launches": st.kernel_launches, "bytes_hashed": st.bytes_hashed,
                 "h2d_bytes": st.h2d_bytes, "d2h_bytes": st.d2h_bytes, "src_bytes_read": st.src_bytes_read,
-                "open_files": st.open_files, "direct_h2d_bytes": st.direct_h2d_bytes}
+                "open_files": st.open_files}
 
     def trace_enable(self, on: bool = True):
         self._check(self._lib.mxd_trace_enable(self._ctx, 1 if on else 0), "mxd_trace_enable")

@@ -1,5 +1,6 @@
 """Developer tool: file -> tree digest GB/s (mxd_tree_digest_file on a page-cache resident tmpfs file) under the current
-environment: MXD_HOST_FEED=stage|map|auto, MXD_MAP_THREADS, MXD_MAP_WINDOW, MXD_MAP_DEPTH, MXD_STAGE_THREADS; wrap in
+environment (MXD_STAGE_THREADS, MXD_STAGE_PIECE, MXD_RING_BYTES; the MXD_HOST_FEED=map experiment of round 2 -- pinning
+the mapped file window by window instead of staging it -- was measured with this tool and removed); wrap in
 `taskset -c 0-1` to see the CPU-starved case (8 ranks sharing a 16-CPU quota)."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -25,6 +26,4 @@ for _ in range(reps):
 dt = (time.perf_counter() - t0) / reps
 tag = " ".join(f"{k}={v}" for k, v in sorted(os.environ.items()) if k.startswith("MXD_"))
 cpus = len(os.sched_getaffinity(0))
-s1 = eng.stats()
-direct = (s1["direct_h2d_bytes"] - s0["direct_h2d_bytes"]) / max(1, s1["h2d_bytes"] - s0["h2d_bytes"])
-print(f"[{tag or 'defaults'}] direct={direct:.2f} cpus={cpus} {size/1e9:g} GB  {dt*1e3:8.1f} ms  {size/dt/1e9:6.1f} GB/s  root {modelx_b200.digest_string(root)[:23]}", flush=True)
+print(f"[{tag or 'defaults'}] cpus={cpus} {size/1e9:g} GB  {dt*1e3:8.1f} ms  {size/dt/1e9:6.1f} GB/s  root {modelx_b200.digest_string(root)[:23]}", flush=True)
