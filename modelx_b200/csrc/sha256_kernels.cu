@@ -144,9 +144,10 @@ __device__ __forceinline__ void absorb(const uint8_t* ptr, const uint64_t nfull,
 }
 
 // MINB = resident CTAs per SM the register allocator must allow (12 x 64 threads -> 80 registers, 16 -> 63).
-template <int MINB>
-__global__ void __launch_bounds__(kThreads, MINB) k_sha256_lanes(const MsgJob j) {
-    const uint64_t m = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+// THREADS: 64, or 32 (MXD_TUNE_CTA=32: one warp per CTA, 24 CTAs per SM -- a finer completion quantum for the drain).
+template <int MINB, int THREADS = kThreads>
+__global__ void __launch_bounds__(THREADS, MINB) k_sha256_lanes(const MsgJob j) {
+    const uint64_t m = (uint64_t)blockIdx.x * THREADS + threadIdx.x;
     const uint32_t one = j.one;
     const Located L = locate(j, m);
     const uint8_t* ptr = L.ptr;
@@ -196,13 +197,16 @@ __global__ void __launch_bounds__(kThreads, MINB) k_sha256_lanes(const MsgJob j)
 // (spans or segments, chained state, per-message control bytes), same results bit for bit.
 // =====================================================================================================
 constexpr int kCoopStages = 2;
-#ifndef MXD_COOP_SHORT_CHAIN
-#define MXD_COOP_SHORT_CHAIN 1
-#endif
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(nthreads) : "memory"); }
 
+// VARIANT: how the chain warp writes one round (same arithmetic, different dependency shape; MXD_TUNE_CHAIN selects):
+//   0  one addition behind Sigma1 on the e-chain, T1 shared by both outputs                     (round 1's choice)
+//   1  the textbook form: T1 = h+K+W+Ch+Sigma1, e' = d+T1, a' = T1+Sigma0+Maj (6 additions)
+//   2  d pre-added: x = (W+K+h)+d is ready before e is, e' = (x+Ch)+Sigma1, T1 = e'-d; the e-chain is
+//      SHF -> LOP3 -> IMAD = 13 clk instead of 17, so the round is bound by the ALU pipe (20 clk), not by latency
+template <int VARIANT>
 __global__ void __launch_bounds__(64) k_sha256_chains_coop(const MsgJob j) {
     // wk[stage][t/4][lane] = {W+K for rounds 4g..4g+3} of that lane's current block
     __shared__ uint4 wk[kCoopStages][16][32];
@@ -314,6 +318,8 @@ __global__ void __launch_bounds__(64) k_sha256_chains_coop(const MsgJob j) {
     }
 
     // ---------------- chain warp: 64 rounds per block on W+K from shared memory ------------------------
+    const uint32_t minus_one = 0u - one;          // opaque like `one`: keeps the subtraction an IMAD
+    (void)minus_one;
     uint32_t h[8];
     if (L.load_state) {
 #pragma unroll
@@ -338,7 +344,16 @@ __global__ void __launch_bounds__(64) k_sha256_chains_coop(const MsgJob j) {
                     uint32_t& a = s[(0 - t) & 7]; uint32_t& bb = s[(1 - t) & 7]; uint32_t& c = s[(2 - t) & 7];
                     uint32_t& d = s[(3 - t) & 7]; uint32_t& e = s[(4 - t) & 7]; uint32_t& f = s[(5 - t) & 7];
                     uint32_t& gg = s[(6 - t) & 7]; uint32_t& hh = s[(7 - t) & 7];
-#if MXD_COOP_SHORT_CHAIN
+                    if constexpr (VARIANT == 2) {
+                        const uint32_t wkh = add_fma(wkq[q], hh, one);
+                        const uint32_t x = add_fma(wkh, d, one);                 // no dependence on e: off the critical path
+                        const uint32_t y = add_fma(x, ch(e, f, gg), one);
+                        const uint32_t enew = add_fma(y, big_sigma1(e), one);
+                        const uint32_t t1 = add_fma(d, minus_one, enew);          // T1 = e' - d
+                        const uint32_t z = add_fma(t1, maj(a, bb, c), one);
+                        hh = add_fma(z, big_sigma0(a), one);
+                        d = enew;
+                    } else if constexpr (VARIANT == 0) {
                     // latency-bound warp: keep only one addition behind Sigma1 on the e-chain (one extra IMAD per round)
                     uint32_t y = add_fma(wkq[q], hh, one);
                     y = add_fma(y, ch(e, f, gg), one);
@@ -348,14 +363,14 @@ __global__ void __launch_bounds__(64) k_sha256_chains_coop(const MsgJob j) {
                     d = add_fma(x, s1, one);
                     const uint32_t z2 = add_fma(z, s1, one);
                     hh = add_fma(z2, big_sigma0(a), one);
-#else
+                    } else {
                     uint32_t t1 = add_fma(wkq[q], hh, one);
                     t1 = add_fma(t1, ch(e, f, gg), one);
                     t1 = add_fma(t1, big_sigma1(e), one);
                     d = add_fma(d, t1, one);
                     const uint32_t t2 = add_fma(big_sigma0(a), maj(a, bb, c), one);
                     hh = add_fma(t1, t2, one);
-#endif
+                    }
                 }
             }
 #pragma unroll
@@ -632,7 +647,18 @@ cudaError_t launch_sha256(const MsgJob& job, cudaStream_t stream) {
     if (job.nmsg <= (uint64_t)g_coop_max) {
         const uint64_t cblocks = (job.nmsg + 31) / 32;
         ++g_launches;
-        k_sha256_chains_coop<<<(unsigned)cblocks, 64, 0, stream>>>(job);
+        static const int chain = [] { const char* e = getenv("MXD_TUNE_CHAIN"); return e ? atoi(e) : 0; }();
+        if (chain == 2)      k_sha256_chains_coop<2><<<(unsigned)cblocks, 64, 0, stream>>>(job);
+        else if (chain == 1) k_sha256_chains_coop<1><<<(unsigned)cblocks, 64, 0, stream>>>(job);
+        else                 k_sha256_chains_coop<0><<<(unsigned)cblocks, 64, 0, stream>>>(job);
+        return cudaGetLastError();
+    }
+    static const int cta = [] { const char* e = getenv("MXD_TUNE_CTA"); return e ? atoi(e) : 64; }();
+    if (cta == 32) {
+        const uint64_t b32 = (job.nmsg + 31) / 32;
+        if (b32 > 0x7fffffffull) return cudaErrorInvalidValue;
+        ++g_launches;
+        k_sha256_lanes<24, 32><<<(unsigned)b32, 32, 0, stream>>>(job);
         return cudaGetLastError();
     }
     if (g_minb == 8)      { ++g_launches; k_sha256_lanes<16><<<(unsigned)blocks, kThreads, 0, stream>>>(job); }
