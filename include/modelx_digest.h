@@ -116,7 +116,10 @@ int mxd_sha256_files(mxd_ctx*, const char* const* paths, uint64_t n, uint8_t* ou
  * e.g. {0,size} and every calcParts range (extension_s3.go:99-112) -- and may tee every byte of the file to a sink
  * (a part uploader / store writer): the file is then read from disk ONCE, where the reference reads it once to hash
  * (push.go:160) and once more to upload (extension_s3.go:71-82).  All jobs of a call, and all calls in flight from
- * other threads, advance together as lanes of the same GPU rounds.  Sink contract: as mxd_sink_fn below. */
+ * other threads, advance together as lanes of the same GPU rounds.  Sink contract: called with disjoint pieces (<= 4 MiB)
+ * that together cover the file exactly once, possibly concurrently from several threads and in any order; the data pointer
+ * is only valid during the call; a sink must not call back into this library (it runs inside a service round); a non-zero
+ * return fails that file with MXD_ERR_IO. */
 typedef int (*mxd_sink_fn)(void* user, uint64_t offset, const void* data, uint64_t nbytes);
 typedef struct {
     const char* path;

@@ -108,6 +108,10 @@ class Engine:
         child._ctx = C.c_void_p()
         child._parent = self
         self._check(self._lib.mxd_op_begin(self._ctx, C.byref(child._ctx)), "mxd_op_begin")
+        import weakref
+        if not hasattr(self, "_children"):
+            self._children = []
+        self._children.append(weakref.ref(child))     # ended with the engine if the caller forgets (a handle must not outlive its context)
         return child
 
     # -- lifecycle ---------------------------------------------------------------------------
@@ -116,6 +120,10 @@ class Engine:
             if self._parent is not None:
                 self._lib.mxd_op_end(self._ctx)
             else:
+                for ref in getattr(self, "_children", []):
+                    child = ref()
+                    if child is not None:
+                        child.close()
                 self._lib.mxd_close(self._ctx)
             self._ctx = C.c_void_p()
 
