@@ -220,6 +220,15 @@ def push_model(raw_ref: str, directory: str = "", tree: bool = False, repos=None
     version = ref.version or "latest"               # pkg/client/registry.go:34-36
     print(f"Pushing to {ref} ")
     store = _store_of(ref)
+    if not tree:
+        # routing advice (mxd_batch_pays_off): a whole-file SHA-256 is one serial chain, ~0.07 GB/s on a GPU lane
+        import modelx_b200
+        sizes = [os.path.getsize(os.path.join(directory, n)) for n in os.listdir(directory)
+                 if not n.startswith(".") and os.path.isfile(os.path.join(directory, n))]
+        if sizes and not modelx_b200.batch_pays_off(len(sizes), sum(sizes), max(sizes)) and max(sizes) > (256 << 20):
+            print(f"note: {len(sizes)} blob(s), largest {max(sizes)/1e9:.1f} GB: reference-identical (whole-file) digests are serial "
+                  "chains and hash faster on CPU cores than on the GPU below ~64 blobs; `--tree` uses the chunked identity "
+                  "(whole GPU, read once)", file=sys.stderr)
     with _engine(lib_path) as eng:
         reg = LocalRegistry(store, eng)
         cl = Client(eng)
