@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <fcntl.h>
 #include <fstream>
+#include <memory>
 #include <sys/resource.h>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -162,12 +163,14 @@ int sink_pieces(const Source& s, uint64_t off, uint64_t n, const uint8_t* data, 
 int source_stage(Core* c, const Source& s, uint64_t off, uint64_t n, uint8_t* dst, const uint8_t** from, StagePool* pool) {
     if (s.fd < 0 && s.pinned) { *from = s.mem + off; return MXD_OK; }
     *from = dst;
-    static const uint64_t kPiece = [] { const char* e = getenv("MXD_STAGE_PIECE"); uint64_t v = e ? strtoull(e, nullptr, 10) : 0; return v >= 4096 ? v : (4ull << 20); }();
+    static const uint64_t kPiece = [] { const char* e = getenv("MXD_STAGE_PIECE"); uint64_t v = e ? strtoull(e, nullptr, 10) : 0; return v >= 4096 ? v : (1ull << 20); }();
     const int pieces = (int)((n + kPiece - 1) / kPiece);
     std::atomic<int> err{0};
     auto fill = [&](int i) {
         const uint64_t p0 = (uint64_t)i * kPiece, pn = std::min(kPiece, n - p0);
-        if (s.fd >= 0) {
+        if (s.map) {          // mapped file: streaming-store copy out of the page cache, under the SIGBUS guard
+            if (stage_copy_mapped(dst + p0, s.map + off + p0, pn) != 0) err.store(-1);
+        } else if (s.fd >= 0) {
             uint64_t got = 0;
             while (got < pn) {
                 ssize_t r = pread(s.fd, dst + p0 + got, pn - got, (off_t)(s.base + off + p0 + got));
@@ -176,13 +179,13 @@ int source_stage(Core* c, const Source& s, uint64_t off, uint64_t n, uint8_t* ds
                 got += (uint64_t)r;
             }
         } else {
-            memcpy(dst + p0, s.mem + off + p0, pn);
+            stage_copy(dst + p0, s.mem + off + p0, pn);
         }
     };
     if (pool && pieces > 1) pool->parallel_for(pieces, fill);
     else for (int i = 0; i < pieces; ++i) fill(i);
     const int e = err.load();
-    if (e == -1) return fail(MXD_ERR_IO, "pread: file shrank while hashing");
+    if (e == -1) return fail(MXD_ERR_IO, "read: file shrank while hashing");
     if (e) return fail(MXD_ERR_IO, std::string("pread: ") + strerror(e));
     c->src_read += n;
     return MXD_OK;
@@ -427,6 +430,7 @@ int host_tree_chunks_all(Core* c, const CancelScope& cs, const Tree& t, const So
         Source piece = src;
         if (piece.fd >= 0) piece.base += b0; else piece.mem += b0;
         piece.sink_base += b0;
+        FileMapGuard fm; fm.attach(&piece, b1 - b0);        // unmapped after stream_tree_chunks has synchronised
         uint8_t* d_chunks = nullptr;
         cudaError_t e = cudaMallocAsync(&d_chunks, (c1 - c0) * 32, d->compute);
         if (e != cudaSuccess) { rcs[g] = MXD_ERR_CUDA; errs[g] = cudaGetErrorString(e); return; }
@@ -468,7 +472,9 @@ int tree_files_on_device(Core* c, const CancelScope& cs, DevState* d, const Tree
     int rc = MXD_OK;
     const uint32_t fused = fused_levels(t, d->slot_bytes);
     const uint64_t span = ipow(t.fanout, fused);
+    std::vector<std::unique_ptr<FileMapGuard>> maps;
     for (size_t k = 0; k < items.size() && rc == MXD_OK; ++k) {
+        if (maps.size() > 64) maps.erase(maps.begin(), maps.begin() + 32);     // staged bytes of old files are long since copied
         TreeFileItem& it = *items[k];
         int fd = open(it.path, O_RDONLY | O_CLOEXEC);
         struct stat st;
@@ -485,7 +491,8 @@ int tree_files_on_device(Core* c, const CancelScope& cs, DevState* d, const Tree
         if (e == cudaSuccess) e = cudaMallocAsync(&d_chunks, nchunks * 32 + 32, d->compute);
         if (e != cudaSuccess) { close(fd); rc = fail(MXD_ERR_CUDA, std::string("cudaMallocAsync: ") + cudaGetErrorString(e)); break; }
         Source src; src.fd = fd;
-        int r = stream_leaves(c, cs, d, t, fused, src, it.size, d_lvl, &cur);
+        maps.emplace_back(new FileMapGuard()); maps.back()->attach(&src, it.size);   // the fills of this file are done when stream_leaves returns,
+        int r = stream_leaves(c, cs, d, t, fused, src, it.size, d_lvl, &cur);         // but keep it simple: unmap after the final sync
         close(fd);
         if (r == MXD_OK) {
             if ((int)fused == t.klevel) e = cudaMemcpyAsync(d_chunks, d_lvl, nchunks * 32, cudaMemcpyDeviceToDevice, d->compute);

@@ -75,6 +75,18 @@ struct Source {
     mxd_sink_fn sink = nullptr;    // every streamed byte is also handed to this callback, once
     void* sink_user = nullptr;
     uint64_t sink_base = 0;        // logical offset of this source's byte 0 for the sink
+    const uint8_t* map = nullptr;  // file sources: read-only mapping of the source's byte 0 onwards (null: pread)
+};
+
+// host/stage_copy.cpp: the staging copy (streaming stores) and file mappings with a SIGBUS guard
+void stage_copy(uint8_t* dst, const uint8_t* src, size_t n);
+int stage_copy_mapped(uint8_t* dst, const uint8_t* src, size_t n);      // -1: the mapping faulted (file shrank)
+void* file_map(int fd, uint64_t base, uint64_t nbytes, const uint8_t** map, uint64_t* handle_len);
+void file_unmap(void* handle, uint64_t handle_len);
+struct FileMapGuard {     // scoped mapping of a Source's file range
+    void* h = nullptr; uint64_t len = 0;
+    void attach(Source* s, uint64_t nbytes) { if (s->fd >= 0 && !s->map) h = file_map(s->fd, s->base, nbytes, &s->map, &len); }
+    ~FileMapGuard() { file_unmap(h, len); }
 };
 
 struct LaneService;

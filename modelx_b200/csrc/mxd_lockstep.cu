@@ -49,6 +49,7 @@ struct Stream {
     Source src;
     int fd = -1;
     uint64_t size = 0;
+    FileMapGuard fmap;                        // read-only mapping of the file (null: pread)
     std::vector<Chain> chains;
     uint64_t pos = 0;                         // bytes below pos have been staged and handed to the sink
     int unfinished = 0;                       // chains that have not had their final round yet
@@ -185,6 +186,7 @@ struct LaneService {
             }
             s->fd = fd; s->src.fd = fd;
             pending_bytes -= s->size; s->size = (uint64_t)st.st_size; pending_bytes += s->size;
+            s->fmap.attach(&s->src, s->size);
         } else {
             s->src.mem = rq->mem;
         }
@@ -241,7 +243,7 @@ struct LaneService {
 
         struct Fill { Stream* s; uint64_t off, n, dst; };      // source bytes [off, off+n) -> h_slot + dst
         std::vector<Fill> fills;
-        constexpr uint64_t kPiece = 4ull << 20;
+        constexpr uint64_t kPiece = 1ull << 20;
         for (Stream* s : active) {
             // window: from the lowest byte any running chain (or the sink) still needs, one share long
             uint64_t a = ~0ull;
@@ -284,7 +286,9 @@ struct LaneService {
             const Fill& fl = fills[f];
             Stream* s = fl.s;
             uint8_t* dst = h_slot + fl.dst;
-            if (s->fd >= 0) {
+            if (s->src.map) {
+                if (stage_copy_mapped(dst, s->src.map + fl.off, fl.n) != 0) { ferr[f] = "read: file shrank while hashing"; s->fill_err.store(1); return; }
+            } else if (s->fd >= 0) {
                 uint64_t got = 0;
                 while (got < fl.n) {
                     ssize_t r = pread(s->fd, dst + got, fl.n - got, (off_t)(fl.off + got));
@@ -293,7 +297,7 @@ struct LaneService {
                     got += (uint64_t)r;
                 }
             } else {
-                memcpy(dst, s->src.mem + fl.off, fl.n);
+                stage_copy(dst, s->src.mem + fl.off, fl.n);
             }
             if (s->src.sink) {                                  // hand each byte to the tee exactly once
                 const uint64_t lo = std::max(fl.off, s->pos), hi = fl.off + fl.n;

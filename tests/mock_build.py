@@ -10,7 +10,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 MOCK = os.path.join(ROOT, "tests", "mock")
 OUT = os.path.join(MOCK, "_build", "libmodelxdigest_mock.so")
 CSRC = os.path.join(ROOT, "modelx_b200", "csrc")
-HOST_SOURCES = ["mxd_api.cu", "mxd_lockstep.cu", "mxd_hasher.cu", os.path.join("host", "client_host.cpp")]
+HOST_SOURCES = ["mxd_api.cu", "mxd_lockstep.cu", "mxd_hasher.cu", os.path.join("host", "client_host.cpp"),
+                os.path.join("host", "stage_copy.cpp")]
 
 
 def build(sanitize: str = "") -> str:

@@ -188,3 +188,33 @@ def test_c_program_cancels_one_of_three(backend, tmp_path):
         args += [p, w.hex()]
     out = subprocess.run(args, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and out.stdout.strip().endswith("PASS"), out.stdout + out.stderr
+
+
+def test_file_truncated_while_hashing_is_an_error_not_a_crash(any_engine, tmp_path):
+    """Files are staged out of a read-only mapping (streaming-store copy); a file that shrinks under the hash must come
+    back as an I/O error ("file shrank"), exactly like the pread path, and not as a SIGBUS that kills the host process."""
+    p = tmp_path / "shrinking.bin"
+    p.write_bytes(os.urandom(40_000_000))
+    calls = []
+
+    def sink(off, piece):
+        if not calls:
+            os.truncate(p, 4096)            # the bytes of the following rounds are gone
+        calls.append(off)
+    res = any_engine.sha256_file_jobs([{"path": str(p), "sink": sink}])
+    assert res[0]["status"] == -4
+    p.write_bytes(os.urandom(40_000_000))
+    first = []
+
+    def sink2(off, piece):
+        if not first:
+            os.truncate(p, 4096)
+        first.append(off)
+    with modelx_b200.Engine(devices=[0], ring_bytes=4 << 20, lib_path=any_engine._lib._name) as small:   # 1 MiB slots: many fills
+        with pytest.raises(modelx_b200.MxdError) as ei:
+            small.tree_digest_file_tee(str(p), sink2, 1 << 20, 16 << 10, 8)
+    assert ei.value.status == -4 and "shrank" in ei.value.detail
+    good = tmp_path / "good.bin"            # the engine (and the process) are fine afterwards
+    data = os.urandom(3_000_000)
+    good.write_bytes(data)
+    assert any_engine.sha256_file(str(good))[0] == hashlib.sha256(data).digest()
