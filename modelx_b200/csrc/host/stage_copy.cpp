@@ -4,11 +4,16 @@
 // byte the CPU copies crosses DRAM as a source read, a read-for-ownership of the destination line, its write-back, and the
 // copy engine's read.  Measured on the bench box (tools/ubench/copy_probe.c, profiles/r02_ring_sweep_and_copy_probe.txt),
 // 16 threads, tmpfs file: pread 36.6 GB/s, memcpy out of an mmap 40 GB/s, AVX2 loads + NON-TEMPORAL stores out of an mmap
-// 56.8 GB/s (no RFO, no cache pollution; 4 threads: 18 / 19 / 27-31 GB/s).  So files are mapped and copied with streaming
-// stores.  A mapping can fault if the file is truncated while it is being hashed (pread would return a short read): the
-// copy runs under a SIGBUS guard that turns the fault into "file shrank while hashing" instead of killing the host
-// process; the handler chains to whatever was installed before for faults that are not ours, and is installed with
-// SA_ONSTACK so that it is safe under the Go runtime.  MXD_STAGE_MMAP=0 restores plain pread.
+// 56.8 GB/s (no RFO, no cache pollution; 4 threads: 18 / 19 / 27-31 GB/s).  In a bare process, that is.  Inside the library
+// the picture flips (profiles/r02_stage_copy_ab.txt, 24 GB file): pread 47.5 GB/s, mapped + streaming stores 32 GB/s,
+// mapped + memcpy 31 GB/s with 16 filler threads -- a process that holds a CUDA context pays far more per page fault
+// (the driver's MMU notifiers), and a fresh mapping of the file is all page faults; only when CPUs are scarce does the
+// cheaper copy win (2 CPUs: 11.4 vs 9.7 GB/s, 4 CPUs: 19.8 vs 18.8).  So the DEFAULT stays pread + memcpy, and
+// MXD_STAGE_MMAP=1 selects the mapped streaming-store copy for CPU-starved hosts.
+// A mapping can fault if the file is truncated while it is being hashed (pread would return a short read): the mapped copy
+// runs under a SIGBUS guard that turns the fault into "file shrank while hashing" instead of killing the host process;
+// the handler chains to whatever was installed before for faults that are not ours, and is installed with SA_ONSTACK so
+// that it is safe under the Go runtime.
 #include <atomic>
 #include <csetjmp>
 #include <csignal>
@@ -42,7 +47,8 @@ __attribute__((target("avx2"))) void copy_nt_avx2(uint8_t* dst, const uint8_t* s
     _mm_sfence();            // the streamed lines are globally visible before the slot is handed to the copy engine
 }
 
-const bool g_avx2 = __builtin_cpu_supports("avx2") && getenv("MXD_STAGE_NO_NT") == nullptr;
+const bool g_mmap = [] { const char* e = getenv("MXD_STAGE_MMAP"); return e && e[0] == '1'; }();
+const bool g_avx2 = g_mmap && __builtin_cpu_supports("avx2") && getenv("MXD_STAGE_NO_NT") == nullptr;
 
 thread_local sigjmp_buf* t_guard = nullptr;
 struct sigaction g_prev_bus;
@@ -85,8 +91,7 @@ int stage_copy_mapped(uint8_t* dst, const uint8_t* src, size_t n) {
 }
 
 bool stage_mmap_enabled() {
-    static const bool on = [] { const char* e = getenv("MXD_STAGE_MMAP"); return !(e && e[0] == '0'); }();
-    return on;
+    return g_mmap;
 }
 
 // Map bytes [base, base + nbytes) of fd read-only; *map = address of byte `base`.  Returns the handle for file_unmap or null.

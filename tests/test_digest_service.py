@@ -190,9 +190,21 @@ def test_c_program_cancels_one_of_three(backend, tmp_path):
     assert out.returncode == 0 and out.stdout.strip().endswith("PASS"), out.stdout + out.stderr
 
 
-def test_file_truncated_while_hashing_is_an_error_not_a_crash(any_engine, tmp_path):
-    """Files are staged out of a read-only mapping (streaming-store copy); a file that shrinks under the hash must come
-    back as an I/O error ("file shrank"), exactly like the pread path, and not as a SIGBUS that kills the host process."""
+@pytest.mark.parametrize("mapped", ["0", "1"])
+def test_file_truncated_while_hashing_is_an_error_not_a_crash(backend, tmp_path, monkeypatch, mapped):
+    """A file that shrinks under the hash must come back as an I/O error ("file shrank") on both staging paths: pread
+    (default) and the opt-in mapped streaming-store copy (MXD_STAGE_MMAP=1), where it would otherwise be a SIGBUS that
+    kills the host process.  (The knob is read once per process: the mapped case runs in a subprocess.)"""
+    if mapped == "1":
+        import subprocess
+        import sys
+        env = dict(os.environ, MXD_STAGE_MMAP="1", MXD_TRUNC_CHILD="1")
+        out = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-p", "no:cacheprovider", __file__, "-k",
+                              "truncated and " + ("mock" if backend else "cuda") + " and 0", "-m", "gpu or not gpu"],
+                             env=env, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+        return
+    any_engine = modelx_b200.Engine(devices=[0], lib_path=backend)
     p = tmp_path / "shrinking.bin"
     p.write_bytes(os.urandom(40_000_000))
     calls = []
@@ -218,3 +230,4 @@ def test_file_truncated_while_hashing_is_an_error_not_a_crash(any_engine, tmp_pa
     data = os.urandom(3_000_000)
     good.write_bytes(data)
     assert any_engine.sha256_file(str(good))[0] == hashlib.sha256(data).digest()
+    any_engine.close()
