@@ -226,8 +226,37 @@ def run_reference(args):
 # ==================================================================================================
 # helpers of this repo's arm
 # ==================================================================================================
-def write_device_range_to_file(torch, blob, nbytes, path, file_offset, threads=8):
-    """Untimed setup: device bytes -> file (pinned bounce buffer, parallel pwrite)."""
+def gpu_local_cpus(gpu_index: int):
+    """CPUs on the NUMA node the GPU hangs off (sysfs local_cpulist of its PCI function), or None."""
+    try:
+        out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(gpu_index)],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        bus = out[-12:] if len(out) >= 12 else out          # "00000000:1b:00.0" -> "0000:1b:00.0"
+        with open(f"/sys/bus/pci/devices/{bus}/local_cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        return (cpus & allowed) or None
+    except (OSError, ValueError, subprocess.SubprocessError):
+        return None
+
+
+def write_device_range_to_file(torch, blob, nbytes, path, file_offset, threads=8, cpus=None):
+    """Untimed setup: device bytes -> file (pinned bounce buffer, parallel pwrite).  With `cpus` the writer threads run on
+    those CPUs, so the page cache pages of this range are first-touched on that NUMA node."""
+    old = os.sched_getaffinity(0)
+    if cpus:
+        os.sched_setaffinity(0, cpus)        # threads created below inherit it
+    try:
+        _write_device_range_to_file(torch, blob, nbytes, path, file_offset, threads)
+    finally:
+        if cpus:
+            os.sched_setaffinity(0, old)
+
+
+def _write_device_range_to_file(torch, blob, nbytes, path, file_offset, threads):
     piece = 512 << 20
     host = torch.empty(piece, dtype=torch.uint8, pin_memory=True)
     fd = os.open(path, os.O_WRONLY)
@@ -419,7 +448,7 @@ def run_b200(args):
                 f.truncate(size)
         barrier()
         if my_bytes:
-            write_device_range_to_file(torch, blob, my_bytes, blob_path, b0)
+            write_device_range_to_file(torch, blob, my_bytes, blob_path, b0, cpus=gpu_local_cpus(local))
         barrier()
         t_file = time.perf_counter() - t_file
 
@@ -460,7 +489,8 @@ def run_b200(args):
                "file_bytes_read_per_step": int(hb[2] / args.steps),
                "ms_per_step": dt_max / args.steps * 1e3, "warmup": e2e_warm,
                "leaf_kernel_ms_per_step": prof_e2e["kernel_ms"] / args.steps, "leaf_launches_per_step": prof_e2e["launches"] / args.steps,
-               "source": f"file on tmpfs ({shm_dir()}, page-cache resident, {size/1e9:g} GB, written in {t_file:.1f} s of untimed setup); "
+               "source": f"file on tmpfs ({shm_dir()}, page-cache resident, {size/1e9:g} GB, written in {t_file:.1f} s of untimed setup, each rank's "
+                         "range first-touched on its GPU's NUMA node); "
                          "each rank preads its chunk range into the library's pinned ring (4 x 64 MiB slots, filler threads bound "
                          "to the GPU's NUMA node), H2D on a copy stream, leaf kernels on a compute stream",
                "api": "mxd_tree_chunks_file(path, rank's byte range) [+ NCCL all-gather of 32 B/chunk] + mxd_tree_finish",
