@@ -48,7 +48,7 @@ typedef struct { const void* ptr; uint64_t len; } mxd_span;   /* host or device 
 typedef struct { int64_t offset, length; } mxd_part;          /* PartRange{offset,length}, extension_s3.go:91-97 */
 
 typedef struct {
-    uint64_t kernel_launches;   /* SHA-256 / compare / generator kernels launched by this context */
+    uint64_t kernel_launches;   /* kernels this library has launched in this process (every launch counts one) */
     uint64_t bytes_hashed;      /* message bytes submitted to the SHA-256 kernel */
     uint64_t h2d_bytes, d2h_bytes;
     uint64_t src_bytes_read;    /* bytes read from files / copied out of host buffers into the pinned ring (read-once accounting) */
@@ -66,6 +66,8 @@ typedef struct {
  *   MXD_MAX_OPEN_FILES  files the whole-message digest service may hold open at once (default RLIMIT_NOFILE/2 - 32, capped at 4096)
  *   MXD_TUNE_COOP       largest launch (in messages) that uses the two-warp cooperative kernel (default 32768, 0 = never)
  *   MXD_TUNE_MINB=8     select the 63-register build of the lanes kernel (A/B profiling only)
+ *   MXD_TUNE_CHAIN=1|2  other ways of writing the round in the two-warp chain kernel; MXD_TUNE_CTA=32: one-warp CTAs in the lanes
+ *                       kernel (both measured: no gain; A/B only)
  *   MXD_TUNE_LEAF_SCHED=2       leaf kernel as a persistent grid with a static per-SM round schedule (measured slower; A/B only)
  *   MXD_TUNE_FUSE=1             first tree levels inside the leaf kernel (measured slower: 8-lane warps hold the ALU pipe; A/B only) */
 
