@@ -21,3 +21,8 @@ print(out.stderr[-4000:], end="")
 sys.exit(out.returncode)
 PY
 rm -rf $W
+echo "--- mixed load driven from Python (libtsan preloaded; only the library is instrumented)"
+LD_PRELOAD=$(gcc -print-file-name=libtsan.so) TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0" python tools/tsan_mixed.py "$LIB" > /tmp/tsan_mixed.$$ 2>&1 || true
+tail -1 /tmp/tsan_mixed.$$
+echo "ThreadSanitizer reports: $(grep -c 'WARNING: ThreadSanitizer' /tmp/tsan_mixed.$$)"
+rm -f /tmp/tsan_mixed.$$
