@@ -596,6 +596,11 @@ int untgz_file(const std::string& archive, const std::string& intodir) {
             if (rc == MXD_OK && padded > size) { char pad[512]; if (!rd(pad, padded - size)) rc = fail(MXD_ERR_IO, "untgz: truncated archive"); }
         } else if (type == '2') {
             const std::string target(h + 157, strnlen(h + 157, 100));
+            // a link may only point inside its own subtree: an absolute or ../ target would let a later entry write
+            // through it to a place outside intodir
+            bool tbad = target.empty() || target[0] == '/';
+            { size_t p2 = 0; while (!tbad && p2 <= target.size()) { size_t q = target.find('/', p2); if (q == std::string::npos) q = target.size(); if (target.substr(p2, q - p2) == "..") tbad = true; p2 = q + 1; } }
+            if (tbad) { rc = fail(MXC_ERR_MANIFEST, "untgz: symlink '" + name + "' -> '" + target + "' would leave the target directory"); break; }
             rc = mkdir_all(dir_of(dst), 0755);
             unlink(dst.c_str());
             if (rc == MXD_OK && symlink(target.c_str(), dst.c_str()) != 0) rc = fail_errno("symlink " + dst);

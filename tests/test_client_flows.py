@@ -119,6 +119,16 @@ def test_directory_blobs_are_packed_pushed_and_pulled(any_engine, tmp_path):
     with pytest.raises(modelx_b200.MxdError):
         client.untgz(str(evil), str(tmp_path / "x"), lib=any_engine._lib)
     assert not (tmp_path / "escape.txt").exists()
+    evil2 = tmp_path / "evil2.tar.gz"                  # a symlink out of the tree, then a file written "through" it
+    with tarfile.open(evil2, "w:gz") as tf:
+        ln = tarfile.TarInfo("out"); ln.type = tarfile.SYMTYPE; ln.linkname = "../../outside"
+        tf.addfile(ln)
+        ti = tarfile.TarInfo("out/pwned.txt"); ti.size = 1
+        tf.addfile(ti, io.BytesIO(b"x"))
+    (tmp_path / "outside").mkdir()
+    with pytest.raises(modelx_b200.MxdError):
+        client.untgz(str(evil2), str(tmp_path / "y" / "z"), lib=any_engine._lib)
+    assert not (tmp_path / "outside" / "pwned.txt").exists()
 
 
 def test_config1_push_then_pull_through_local_registry(any_engine, tmp_path):
