@@ -33,7 +33,9 @@ def mock_lib():
     """Path of the CPU test double of libmodelxdigest.so (host sources + a synchronous CUDA stand-in + oracle
     hashing, see tests/mock/include/cuda_runtime.h).  Test infrastructure: never loaded by the product."""
     from tests import mock_build
-    return mock_build.build()
+    # MXD_MOCK_SANITIZE=address|thread|address,undefined selects an instrumented build (run pytest with the matching
+    # runtime preloaded, see tools/asan_host_suite.sh)
+    return mock_build.build(os.environ.get("MXD_MOCK_SANITIZE", ""))
 
 
 @pytest.fixture(params=[pytest.param("mock"), pytest.param("cuda", marks=pytest.mark.gpu)])

@@ -15,8 +15,9 @@ HOST_SOURCES = ["mxd_api.cu", "mxd_lockstep.cu", "mxd_hasher.cu", os.path.join("
 
 
 def build(sanitize: str = "") -> str:
-    """sanitize: "" | "thread" | "address" -> a separately named library"""
-    out = OUT if not sanitize else OUT.replace(".so", f"_{sanitize}.so")
+    """sanitize: "" | "thread" | "address" | "address,undefined" -> a separately named library"""
+    tag = sanitize.replace(",", "_")
+    out = OUT if not sanitize else OUT.replace(".so", f"_{tag}.so")
     srcs = [os.path.join(CSRC, f) for f in HOST_SOURCES]
     deps = srcs + [os.path.join(CSRC, f) for f in ("kernels.h", "mxd_core.h")] + \
         [os.path.join(MOCK, "mock_kernels.cpp"), os.path.join(MOCK, "include", "cuda_runtime.h"),
@@ -25,7 +26,7 @@ def build(sanitize: str = "") -> str:
     if os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
         return out
     os.makedirs(os.path.dirname(out), exist_ok=True)
-    objdir = os.path.join(os.path.dirname(out), "obj" + ("_" + sanitize if sanitize else ""))
+    objdir = os.path.join(os.path.dirname(out), "obj" + ("_" + tag if sanitize else ""))
     os.makedirs(objdir, exist_ok=True)
     san = [f"-fsanitize={sanitize}", "-fno-omit-frame-pointer"] if sanitize else []
     objs = []
