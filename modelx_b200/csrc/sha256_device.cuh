@@ -55,12 +55,16 @@ __device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 
 
 // FMA pipe: a + b computed as a*one + b where `one` is an opaque register holding 1.
 // MXD_ADD_ON_ALU=1 switches back to plain adds (ptxas then picks IADD3), kept for A/B profiling.
+// MXD_ADD_IMM=1 writes the 1 as an immediate (mad.lo a,1,b): ptxas then sees through it and turns two thirds of the
+// additions back into IADD3 (SASS of the leaf kernel: 494 IADD3 / 238 IMAD.IADD), which is why the 1 is opaque.
 #ifndef MXD_ADD_ON_ALU
 #define MXD_ADD_ON_ALU 0
 #endif
 __device__ __forceinline__ uint32_t add_fma(uint32_t a, uint32_t b, uint32_t one) {
 #if MXD_ADD_ON_ALU
     (void)one; return a + b;
+#elif defined(MXD_ADD_IMM) && MXD_ADD_IMM
+    (void)one; uint32_t d; asm("mad.lo.u32 %0, %1, 1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d;   // A/B: IMAD.IADD (immediate 1)
 #else
     uint32_t d; asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(b)); return d;
 #endif
