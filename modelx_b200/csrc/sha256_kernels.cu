@@ -196,10 +196,105 @@ __global__ void __launch_bounds__(THREADS, MINB) k_sha256_lanes(const MsgJob j) 
 // Measured 69-73 MB/s per chain against 38 MB/s in the lanes kernel (profiles/r01_batch_bench_coop_v2.txt).  Same MsgJob contract as the lanes kernel
 // (spans or segments, chained state, per-message control bytes), same results bit for bit.
 // =====================================================================================================
+// The producer warp of the two cooperative kernels below: loads / pads block b of its lane's message (next block
+// prefetched into registers), expands the schedule and publishes W[t]+K[t] (t = 0..63) one stage ahead.
+// wk element (stage, t/4, lane) lives at wk[(stage * 16 + t/4) * COLS + lane]; lanes with publish == false compute
+// along (they shadow a live lane) and store nothing.
 constexpr int kCoopStages = 2;
+constexpr int kFull0 = 1, kEmpty0 = 1 + kCoopStages;   // named barrier ids (0 is __syncthreads)
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(nthreads) : "memory"); }
+
+template <int COLS>
+__device__ __forceinline__ void coop_produce(uint4* wk, const int lane, const bool publish, const Located& L, const uint64_t nfull,
+                                             const uint32_t r, const uint64_t nblk, const uint64_t bits, const uint64_t nmax,
+                                             const uint32_t one) {
+    const uint8_t* ptr = L.ptr;
+    // ---------------- producer: load / pad, expand, publish W+K ---------------------------------
+    // expands w[16] to the 64 schedule words, adds the round constants and publishes them for `lane`
+    auto expand_store = [&](uint32_t (&w)[16], int st) {
+        constexpr K256Table K = k256_table();
+#pragma unroll
+        for (int g = 0; g < 16; ++g) {
+            uint32_t o4[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int t = 4 * g + q;
+                if (t >= 16) {
+                    uint32_t x = add_fma(w[t & 15], small_sigma0(w[(t + 1) & 15]), one);
+                    x = add_fma(x, w[(t + 9) & 15], one);
+                    w[t & 15] = add_fma(x, small_sigma1(w[(t + 14) & 15]), one);
+                }
+                o4[q] = add_fma(w[t & 15], K.v[t], one);
+            }
+            if (publish) wk[(st * 16 + g) * COLS + lane] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+        }
+    };
+    const bool warp_aligned = __all_sync(0xffffffffu, (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0);
+    uint32_t w[16];
+    uint64_t b = 0;
+    if (warp_aligned) {
+        // Hot loop (aligned messages): the next block is prefetched into registers while this one is expanded,
+        // so the chain warp never waits for DRAM.  Runs while ANY lane still has full blocks; lanes that ran
+        // out keep re-reading their last block (or nothing) and publish nothing.
+        // Lanes without a message (tail of the batch, finished files) shadow a live lane so that they do not
+        // force the whole warp onto the slow path: same address, same trip count, nothing of theirs is consumed.
+        const unsigned have = __ballot_sync(0xffffffffu, nblk > 0 && nfull > 0);
+        const int src = have ? (__ffs(have) - 1) : 0;
+        const uint64_t src_ptr = __shfl_sync(0xffffffffu, reinterpret_cast<uint64_t>(ptr), src);
+        const uint64_t src_nfull = __shfl_sync(0xffffffffu, nfull, src);
+        const bool shadow = (nblk == 0);      // only lanes the chain warp will never read for
+        const uint8_t* hot_ptr = shadow ? reinterpret_cast<const uint8_t*>(src_ptr) : ptr;
+        const uint64_t hot_nfull = shadow ? src_nfull : nfull;
+        uint64_t nfull_min = have ? hot_nfull : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const uint64_t other = __shfl_xor_sync(0xffffffffu, nfull_min, o); nfull_min = other < nfull_min ? other : nfull_min; }
+        if (nfull_min > 0) {
+            const uint4* p4 = reinterpret_cast<const uint4*>(hot_ptr);
+            uint4 v0 = ldg128(p4), v1 = ldg128(p4 + 1), v2 = ldg128(p4 + 2), v3 = ldg128(p4 + 3);
+            for (; b < nfull_min; ++b) {          // every lane has a full block b here: no divergence, no merges
+                const int st = (int)(b % kCoopStages);
+                if (b >= (uint64_t)kCoopStages) named_bar_sync(kEmpty0 + st, 64);
+                unpack_block(v0, v1, v2, v3, w);
+                p4 += (b + 1 < hot_nfull) ? 4 : 0;
+                v0 = ldg128(p4); v1 = ldg128(p4 + 1); v2 = ldg128(p4 + 2); v3 = ldg128(p4 + 3);
+                expand_store(w, st);
+                named_bar_arrive(kFull0 + st, 64);
+            }
+        }
+    }
+    // Everything else: ragged tails of the batch, unaligned messages, padding and length blocks.
+    for (; b < nmax; ++b) {
+        const int st = (int)(b % kCoopStages);
+        if (b >= (uint64_t)kCoopStages) named_bar_sync(kEmpty0 + st, 64);   // chain warp has drained this stage
+        if (b < nblk) {
+            if (b < nfull) {
+                load_block_unaligned(ptr + (b << 6), w);
+            } else if (b == nfull) {
+                const uint8_t* t = ptr + (nfull << 6);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    uint32_t word = 0;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint32_t idx = 4 * k + q;
+                        if (idx < r) word |= (uint32_t)__ldg(t + idx) << (24 - 8 * q);
+                        else if (idx == r) word |= 0x80u << (24 - 8 * q);
+                    }
+                    w[k] = word;
+                }
+                if (r < 56) { w[14] = (uint32_t)(bits >> 32); w[15] = (uint32_t)bits; }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 14; ++k) w[k] = 0;
+                w[14] = (uint32_t)(bits >> 32); w[15] = (uint32_t)bits;
+            }
+            expand_store(w, st);
+        }
+        named_bar_arrive(kFull0 + st, 64);
+    }
+}
 
 // VARIANT: how the chain warp writes one round (same arithmetic, different dependency shape; MXD_TUNE_CHAIN selects):
 //   0  one addition behind Sigma1 on the e-chain, T1 shared by both outputs                     (round 1's choice)
@@ -215,7 +310,6 @@ __global__ void __launch_bounds__(64) k_sha256_chains_coop(const MsgJob j) {
     const uint64_t m = (uint64_t)blockIdx.x * 32 + lane;
     const uint32_t one = j.one;
     const Located L = locate(j, m);
-    const uint8_t* ptr = L.ptr;
     const uint64_t len = L.len;
     const bool live = L.live;
     const int fin = L.fin;
@@ -228,92 +322,8 @@ __global__ void __launch_bounds__(64) k_sha256_chains_coop(const MsgJob j) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { const uint64_t other = __shfl_xor_sync(0xffffffffu, nmax, o); nmax = other > nmax ? other : nmax; }
 
-    constexpr int kFull0 = 1, kEmpty0 = 1 + kCoopStages;   // named barrier ids (0 is __syncthreads)
-
     if (role == 1) {
-        // ---------------- producer: load / pad, expand, publish W+K ---------------------------------
-        // expands w[16] to the 64 schedule words, adds the round constants and publishes them for `lane`
-        auto expand_store = [&](uint32_t (&w)[16], int st) {
-            constexpr K256Table K = k256_table();
-#pragma unroll
-            for (int g = 0; g < 16; ++g) {
-                uint32_t o4[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int t = 4 * g + q;
-                    if (t >= 16) {
-                        uint32_t x = add_fma(w[t & 15], small_sigma0(w[(t + 1) & 15]), one);
-                        x = add_fma(x, w[(t + 9) & 15], one);
-                        w[t & 15] = add_fma(x, small_sigma1(w[(t + 14) & 15]), one);
-                    }
-                    o4[q] = add_fma(w[t & 15], K.v[t], one);
-                }
-                wk[st][g][lane] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
-            }
-        };
-        const bool warp_aligned = __all_sync(0xffffffffu, (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0);
-        uint32_t w[16];
-        uint64_t b = 0;
-        if (warp_aligned) {
-            // Hot loop (aligned messages): the next block is prefetched into registers while this one is expanded,
-            // so the chain warp never waits for DRAM.  Runs while ANY lane still has full blocks; lanes that ran
-            // out keep re-reading their last block (or nothing) and publish nothing.
-            // Lanes without a message (tail of the batch, finished files) shadow a live lane so that they do not
-            // force the whole warp onto the slow path: same address, same trip count, nothing of theirs is consumed.
-            const unsigned have = __ballot_sync(0xffffffffu, nblk > 0 && nfull > 0);
-            const int src = have ? (__ffs(have) - 1) : 0;
-            const uint64_t src_ptr = __shfl_sync(0xffffffffu, reinterpret_cast<uint64_t>(ptr), src);
-            const uint64_t src_nfull = __shfl_sync(0xffffffffu, nfull, src);
-            const bool shadow = (nblk == 0);      // only lanes the chain warp will never read for
-            const uint8_t* hot_ptr = shadow ? reinterpret_cast<const uint8_t*>(src_ptr) : ptr;
-            const uint64_t hot_nfull = shadow ? src_nfull : nfull;
-            uint64_t nfull_min = have ? hot_nfull : 0;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) { const uint64_t other = __shfl_xor_sync(0xffffffffu, nfull_min, o); nfull_min = other < nfull_min ? other : nfull_min; }
-            if (nfull_min > 0) {
-                const uint4* p4 = reinterpret_cast<const uint4*>(hot_ptr);
-                uint4 v0 = ldg128(p4), v1 = ldg128(p4 + 1), v2 = ldg128(p4 + 2), v3 = ldg128(p4 + 3);
-                for (; b < nfull_min; ++b) {          // every lane has a full block b here: no divergence, no merges
-                    const int st = (int)(b % kCoopStages);
-                    if (b >= (uint64_t)kCoopStages) named_bar_sync(kEmpty0 + st, 64);
-                    unpack_block(v0, v1, v2, v3, w);
-                    p4 += (b + 1 < hot_nfull) ? 4 : 0;
-                    v0 = ldg128(p4); v1 = ldg128(p4 + 1); v2 = ldg128(p4 + 2); v3 = ldg128(p4 + 3);
-                    expand_store(w, st);
-                    named_bar_arrive(kFull0 + st, 64);
-                }
-            }
-        }
-        // Everything else: ragged tails of the batch, unaligned messages, padding and length blocks.
-        for (; b < nmax; ++b) {
-            const int st = (int)(b % kCoopStages);
-            if (b >= (uint64_t)kCoopStages) named_bar_sync(kEmpty0 + st, 64);   // chain warp has drained this stage
-            if (b < nblk) {
-                if (b < nfull) {
-                    load_block_unaligned(ptr + (b << 6), w);
-                } else if (b == nfull) {
-                    const uint8_t* t = ptr + (nfull << 6);
-#pragma unroll
-                    for (int k = 0; k < 16; ++k) {
-                        uint32_t word = 0;
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const uint32_t idx = 4 * k + q;
-                            if (idx < r) word |= (uint32_t)__ldg(t + idx) << (24 - 8 * q);
-                            else if (idx == r) word |= 0x80u << (24 - 8 * q);
-                        }
-                        w[k] = word;
-                    }
-                    if (r < 56) { w[14] = (uint32_t)(bits >> 32); w[15] = (uint32_t)bits; }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 14; ++k) w[k] = 0;
-                    w[14] = (uint32_t)(bits >> 32); w[15] = (uint32_t)bits;
-                }
-                expand_store(w, st);
-            }
-            named_bar_arrive(kFull0 + st, 64);
-        }
+        coop_produce<32>(&wk[0][0][0], lane, true, L, nfull, r, nblk, bits, nmax, one);
         return;
     }
 
@@ -389,6 +399,134 @@ __global__ void __launch_bounds__(64) k_sha256_chains_coop(const MsgJob j) {
     hi.x = bswap32(h[4]); hi.y = bswap32(h[5]); hi.z = bswap32(h[6]); hi.w = bswap32(h[7]);
     uint4* o = reinterpret_cast<uint4*>(j.out + 32 * (uint64_t)L.oidx);
     o[0] = lo; o[1] = hi;
+}
+
+// =====================================================================================================
+// k_sha256_chains_pair: very few chains (at most two CTAs per SM), where only the latency of ONE chain counts:
+// a pushed file, the streamed tar.gz of the incremental hasher, the 32 shards of BASELINE config 3, the 1,000
+// blobs of config 5.  On this GPU a warp instruction holds its 16-lane pipe for 2 clk whatever the number of
+// active lanes (profiles/r02_halfwarp_ubench.txt), so a round's 10 rotate/logic instructions cost 20 clk per warp
+// and the chain warp above cannot go below that.  Here the two halves of a round run in two LANES of the same warp:
+//   E lane (even)  holds e,f,g,h:  e' = Sigma1(e) + Ch(e,f,g) + h + W+K + d
+//   A lane (odd)   holds a,b,c,d:  a' = Sigma0(a) + Maj(a,b,c) + (e' - d)
+// Both are "xor of three rotates of v0, plus a three-input select, plus two additions", so one instruction stream
+// serves both with per-lane registers for what differs: the rotate amounts, Maj(a,b,c) = Ch(a, b|c, b&c) so that
+// the select is the same LOP3 with operands prepared from OLD values (off the critical path), a +-1 multiplier and a
+// zero column of W+K for the A lanes.  7 ALU-pipe instructions per round instead of 10, and a 3-instruction
+// dependency chain (SHF -> LOP3 -> IMAD).  The lanes trade one value per round with ONE shfl.xor: E sends e', A sends
+// a'.  The A lane runs two rounds behind the E lane, so what arrives is needed one iteration later (E needs
+// d(t+1) = a(t-2), A needs e(t+1) - d(t) for its round t): the shuffle latency is off the critical path too.
+// A block is 66 iterations: 64 + the 2 of skew.  16 chains per CTA (chain warp + producer warp as above).
+// Same MsgJob contract and the same results bit for bit as the other two kernels (tests/test_gpu_parity.py runs
+// every small batch through this kernel; tests/pair_pipeline_emulation.py is the dataflow in Python).
+// =====================================================================================================
+constexpr int kPairChains = 16;
+
+template <int LUT>
+__device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d; asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(LUT)); return d;
+}
+__device__ __forceinline__ uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c) {        // a*b+c on the FMA pipe
+    uint32_t d; asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d;
+}
+
+__global__ void __launch_bounds__(64) k_sha256_chains_pair(const MsgJob j) {
+    // wk[stage][t/4][chain]; column kPairChains stays zero: the "W+K" of the A lanes
+    __shared__ uint4 wk[kCoopStages][16][kPairChains + 1];
+    const int lane = threadIdx.x & 31;
+    const int role = threadIdx.x >> 5;            // 0 = chain warp (lanes 2c, 2c+1 serve chain c), 1 = producer warp (lane c)
+    const int chain = role == 1 ? lane : (lane >> 1);
+    const uint64_t m = chain < kPairChains ? (uint64_t)blockIdx.x * kPairChains + chain : ~0ull;
+    const uint32_t one = j.one;
+    const Located L = locate(j, m);
+    const uint64_t len = L.len;
+    const bool live = L.live;
+    const int fin = L.fin;
+    const uint64_t nfull = len >> 6;
+    const uint32_t r = (uint32_t)(len & 63u);
+    const uint64_t nblk = live ? nfull + (fin ? (r >= 56 ? 2u : 1u) : 0u) : 0;
+    const uint64_t bits = (L.prefix + len) << 3;
+    uint64_t nmax = nblk;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const uint64_t other = __shfl_xor_sync(0xffffffffu, nmax, o); nmax = other > nmax ? other : nmax; }
+    if (threadIdx.x < kCoopStages * 16) wk[threadIdx.x >> 4][threadIdx.x & 15][kPairChains] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+
+    if (role == 1) {
+        coop_produce<kPairChains + 1>(&wk[0][0][0], lane, lane < kPairChains, L, nfull, r, nblk, bits, nmax, one);
+        return;
+    }
+
+    // ---------------- chain warp ------------------------------------------------------------------------
+    const bool isE = (lane & 1) == 0;
+    const uint32_t r0 = isE ? 6u : 2u, r1 = isE ? 11u : 13u, r2 = isE ? 25u : 22u;   // Sigma1 / Sigma0
+    const uint32_t coef = isE ? one : 0u - one;
+    const uint32_t mA = isE ? 0u : 0xffffffffu;
+    const int col = isE ? chain : kPairChains;
+    uint32_t hs[4];                               // E lane: H4..H7, A lane: H0..H3
+    if (L.load_state) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) hs[i] = j.state[8 * (uint64_t)L.sidx + (isE ? 4 : 0) + i];
+    } else {
+        uint32_t iv[8];
+        sha256_iv(iv);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) hs[i] = isE ? iv[4 + i] : iv[i];
+    }
+    for (uint64_t b = 0; b < nmax; ++b) {
+        const int st = (int)(b % kCoopStages);
+        named_bar_sync(kFull0 + st, 64);
+        // Every lane runs every block of the longest chain (a finished pair computes on stale W+K and drops the result):
+        // the warp stays converged, so the exchange is a bare SHFL with the full mask.
+        {
+            // window s[]: position p holds variable (p - i) mod 4 at iteration i.  E lane: (e,f,g,h).  A lane: (a,b,c,d),
+            // which starts two rounds "before" round 0 as (H2, H3, -, -) and is fed H1, H0 in the two lead-in iterations,
+            // so that the E lane receives d(1) = H2, d(2) = H1, d(3) = H0 through the ordinary exchange.
+            uint32_t s[4];
+            s[0] = isE ? hs[0] : hs[2]; s[1] = isE ? hs[1] : hs[3]; s[2] = hs[2]; s[3] = hs[3];
+            uint4 v = wk[st][0][col];
+            uint32_t recv = __shfl_xor_sync(0xffffffffu, hs[3], 1);                          // E receives H3 = d(0)
+            uint32_t in1 = add_fma(recv, mad_lo(hs[3], coef, v.x), one);             // E: d(0) + h(0) + W0+K0
+            uint32_t e64[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int i = 0; i < 66; ++i) {
+                uint32_t& v0 = s[(0 - i) & 3]; uint32_t& v1 = s[(1 - i) & 3]; uint32_t& v2 = s[(2 - i) & 3];
+                uint32_t& v3 = s[(3 - i) & 3];
+                recv = __shfl_xor_sync(0xffffffffu, v0, 1);                                 // used in iteration i + 1
+                const int t = i + 1;
+                uint32_t wkx = 0u;
+                if (t < 64) {
+                    if ((t & 3) == 0) v = wk[st][t >> 2][col];
+                    wkx = (t & 3) == 0 ? v.x : (t & 3) == 1 ? v.y : (t & 3) == 2 ? v.z : v.w;
+                }
+                const uint32_t x = xor3(__funnelshift_r(v0, v0, r0), __funnelshift_r(v0, v0, r1), __funnelshift_r(v0, v0, r2));
+                const uint32_t p = lop3<0xF8>(v1, v2, mA);                           // E: f      A: b | c
+                const uint32_t q = lop3<0xC4>(v1, v2, mA);                           // E: g      A: b & c
+                const uint32_t c = ch(v0, p, q);                                     // E: Ch     A: Maj
+                const uint32_t hwm = mad_lo(v2, coef, wkx);                          // E: h(t)+W+K(t)   A: -d(t)
+                const uint32_t in1n = add_fma(recv, hwm, one);
+                uint32_t nw = add_fma(x, add_fma(c, in1, one), one);
+                if (i == 0) nw = isE ? nw : hs[1];
+                if (i == 1) nw = isE ? nw : hs[0];
+                v3 = nw;                                                             // v0 of the next iteration
+                in1 = in1n;
+                if (i == 63) { e64[0] = s[0]; e64[1] = s[1]; e64[2] = s[2]; e64[3] = s[3]; }   // (e,f,g,h) after round 63
+            }
+            // feed-forward (FIPS 180-4 section 6.2.2 step 4).  After iteration 65 the A lane's (a,b,c,d) sit in s[2],s[3],s[0],s[1].
+#pragma unroll
+            for (int k = 0; k < 4; ++k) hs[k] = b < nblk ? add_fma(hs[k], isE ? e64[k] : s[(k + 2) & 3], one) : hs[k];
+        }
+        if (b + kCoopStages < nmax) named_bar_arrive(kEmpty0 + st, 64);
+    }
+    if (!live) return;
+    if (!fin) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) j.state[8 * (uint64_t)L.sidx + (isE ? 4 : 0) + i] = hs[i];
+        return;
+    }
+    uint4 o;
+    o.x = bswap32(hs[0]); o.y = bswap32(hs[1]); o.z = bswap32(hs[2]); o.w = bswap32(hs[3]);
+    reinterpret_cast<uint4*>(j.out + 32 * (uint64_t)L.oidx)[isE ? 1 : 0] = o;
 }
 
 // SHA-256 of a short message given as `nwords` big-endian 32-bit words (nwords a multiple of 8: concatenated
@@ -637,6 +775,9 @@ uint64_t kernel_launch_count() { return g_launches.load(); }
 static int g_minb = [] { const char* e = getenv("MXD_TUNE_MINB"); const int v = e ? atoi(e) : 6; return (v == 8 || v == 4) ? v : 6; }();
 
 static long g_coop_max = [] { const char* e = getenv("MXD_TUNE_COOP"); return e ? atol(e) : 32768L; }();
+// Up to two 16-chain CTAs per SM (148 SMs): every chain warp and producer warp has an SM sub-partition to itself.
+// MXD_TUNE_PAIR=0 disables the pair kernel, =N sets the threshold.
+static long g_pair_max = [] { const char* e = getenv("MXD_TUNE_PAIR"); return e ? atol(e) : 4736L; }();
 
 cudaError_t launch_sha256(const MsgJob& job, cudaStream_t stream) {
     if (job.nmsg == 0) return cudaSuccess;
@@ -644,6 +785,11 @@ cudaError_t launch_sha256(const MsgJob& job, cudaStream_t stream) {
     if (blocks > 0x7fffffffull) return cudaErrorInvalidValue;
     // Few, long chains: two warps per 32 chains (see k_sha256_chains_coop).  Measured crossover with the lanes kernel
     // is between 16k chains (coop 675 vs 610 GB/s) and 64k (791 vs 834).  MXD_TUNE_COOP=0 disables, =N sets the threshold.
+    if (job.nmsg <= (uint64_t)g_pair_max) {
+        ++g_launches;
+        k_sha256_chains_pair<<<(unsigned)((job.nmsg + kPairChains - 1) / kPairChains), 64, 0, stream>>>(job);
+        return cudaGetLastError();
+    }
     if (job.nmsg <= (uint64_t)g_coop_max) {
         const uint64_t cblocks = (job.nmsg + 31) / 32;
         ++g_launches;
