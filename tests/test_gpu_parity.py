@@ -448,3 +448,37 @@ def test_file_part_digests_follow_calc_parts(engine, tmp_path):
     with pytest.raises(modelx_b200.MxdError) as ei:
         engine.sha256_file_parts(str(p), [(len(data) - 10, 11)])
     assert ei.value.status == -4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pair_max", ["0", "100000"])
+def test_small_launch_kernels_agree(tmp_path, pair_max):
+    """Launches of at most 4,736 messages run in k_sha256_chains_pair, up to 32,768 in k_sha256_chains_coop.  A fresh
+    process with MXD_TUNE_PAIR=0 sends everything small through the cooperative kernel, =100000 everything up to 32,768
+    messages through the pair kernel (4 CTAs per SM and more): same digests either way -- ragged batch, files, hasher."""
+    import subprocess
+    import sys
+    script = r'''
+import hashlib, os, random, sys
+import modelx_b200
+rng = random.Random(11)
+eng = modelx_b200.Engine(devices=[0])
+msgs = [rng.randbytes(n) for n in list(range(0, 200)) + [1000, 4095, 4096, 4097, 65536, 1_000_003]]
+assert eng.sha256_batch(msgs) == [hashlib.sha256(m).digest() for m in msgs]
+many = [rng.randbytes(rng.randrange(0, 700)) for _ in range(9000)]            # > 4,736 messages in one launch
+assert eng.sha256_batch(many) == [hashlib.sha256(m).digest() for m in many]
+paths = []
+for i, n in enumerate([0, 1, 63, 64, 5_000_000, 70_000_001, 33]):
+    p = os.path.join(sys.argv[1], f"f{i}"); d = rng.randbytes(n); open(p, "wb").write(d); paths.append((p, hashlib.sha256(d).digest(), n))
+digs, sizes = eng.sha256_files([p for p, _, _ in paths])
+assert digs == [d for _, d, _ in paths] and sizes == [n for _, _, n in paths]
+h = eng.hasher(); ref = hashlib.sha256()
+for n in (0, 1, 63, 64, 65, 100_000, 4 << 20, 3):
+    b = rng.randbytes(n); h.write(b); ref.update(b)
+assert h.sum() == ref.digest()
+print("pair-ok", eng.stats()["kernel_launches"])
+'''
+    env = dict(os.environ, MXD_TUNE_PAIR=pair_max)
+    out = subprocess.run([sys.executable, "-c", script, str(tmp_path)], capture_output=True, text=True, timeout=600, env=env,
+                         cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert out.returncode == 0 and "pair-ok" in out.stdout, out.stdout + out.stderr
