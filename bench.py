@@ -626,7 +626,7 @@ def run_compat(args, eng, torch, dist, dev, world, rank, run_tag, barrier, max_o
     d = os.path.join(shm_dir(), f"modelx_b200_compat_{run_tag}_{rank}")
     os.makedirs(d, exist_ok=True)
     out = {"identity": "whole-file SHA-256, bit-identical to the reference's Descriptor.Digest",
-           "note": "one file = one serial SHA-256 chain = one GPU lane (~0.07-0.1 GB/s); throughput comes only from the number of "
+           "note": "one file = one serial SHA-256 chain (~0.08 GB/s on the GPU); throughput comes only from the number of "
                    "files in flight, so config 3 (32 chains) is slower than three SHA-NI cores and config 5 (1000 chains) is faster; "
                    "adding GPUs adds PCIe lanes and SM sub-partitions but not chains (DESIGN.md section 6)"}
     from tests.oracle_lib import Oracle
