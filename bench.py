@@ -659,7 +659,7 @@ def run_compat(args, eng, torch, dist, dev, world, rank, run_tag, barrier, max_o
             out["config1"] = {"workload": "one 64 MB random blob: digest + PutBlob into the in-process FS registry (+ manifest, index.json)",
                               "gpu_whole_file_identity_ms": times["whole_file"] * 1e3, "gpu_tree_identity_ms": times["tree_keyed"] * 1e3,
                               "cpu_reference_ms": tcpu * 1e3,
-                              "note": "one blob = one serial chain: the reference-identical push is ~20x slower on the GPU than the reference's "
+                              "note": f"one blob = one serial chain: the reference-identical push is {times['whole_file'] / tcpu:.0f}x slower on the GPU than the reference's "
                                       "CPU digest + copy (mxd_batch_pays_off = false: the Go shim keeps it on the CPU); the tree-keyed push of the "
                                       "same blob reads it once and is bound by the store write"}
             shutil.rmtree(m1, ignore_errors=True)
