@@ -65,6 +65,7 @@ typedef struct {
  *   MXD_NO_NUMA_BIND    set to disable binding pinned allocations and filler threads to the device's local CPUs
  *   MXD_MAX_OPEN_FILES  files the whole-message digest service may hold open at once (default RLIMIT_NOFILE/2 - 32, capped at 4096)
  *   MXD_TUNE_COOP       largest launch (in messages) that uses the two-warp cooperative kernel (default 32768, 0 = never)
+ *   MXD_TUNE_PAIR       largest launch (in messages) that uses the two-lanes-per-chain kernel (default 4736 = two CTAs per SM, 0 = never)
  *   MXD_TUNE_MINB=8     select the 63-register build of the lanes kernel (A/B profiling only)
  *   MXD_TUNE_CHAIN=1|2  other ways of writing the round in the two-warp chain kernel; MXD_TUNE_CTA=32: one-warp CTAs in the lanes
  *                       kernel (both measured: no gain; A/B only)
