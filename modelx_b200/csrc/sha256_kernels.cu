@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_sha256_lanes(const MsgJob j) 
 // prefetched into registers), expands the schedule and publishes W[t]+K[t] (t = 0..63) one stage ahead.
 // wk element (stage, t/4, lane) lives at wk[(stage * 16 + t/4) * COLS + lane]; lanes with publish == false compute
 // along (they shadow a live lane) and store nothing.
-constexpr int kCoopStages = 2;
+constexpr int kCoopStages = 2;                     // blocks the producer may run ahead; 3 and 4 measured 2-5 % slower (profiles/r02_coop_stages.txt)
 constexpr int kFull0 = 1, kEmpty0 = 1 + kCoopStages;   // named barrier ids (0 is __syncthreads)
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory"); }
