@@ -556,6 +556,7 @@ int untgz_file(const std::string& archive, const std::string& intodir) {
         longname.clear();
         const uint64_t padded = (size + 511) / 512 * 512;
         if (type == 'L' || type == 'x' || type == 'g') {          // GNU long name / pax headers
+            if (size > (1u << 20)) { rc = fail(MXC_ERR_MANIFEST, "untgz: extended header of " + std::to_string(size) + " bytes"); break; }
             std::string body(padded, '\0');
             if (padded && !rd(&body[0], padded)) { rc = fail(MXD_ERR_IO, "untgz: truncated archive"); break; }
             body.resize(size);
@@ -604,8 +605,13 @@ int untgz_file(const std::string& archive, const std::string& intodir) {
             rc = mkdir_all(dir_of(dst), 0755);
             unlink(dst.c_str());
             if (rc == MXD_OK && symlink(target.c_str(), dst.c_str()) != 0) rc = fail_errno("symlink " + dst);
-        } else if (padded) {                                      // other entry types: skip the body
-            std::string skip(padded, '\0'); if (!rd(&skip[0], padded)) rc = fail(MXD_ERR_IO, "untgz: truncated archive");
+        } else {                                                  // other entry types: skip the body
+            std::vector<char> skip(64 << 10);
+            for (uint64_t left = padded; rc == MXD_OK && left;) {
+                const size_t n = (size_t)std::min<uint64_t>(skip.size(), left);
+                if (!rd(skip.data(), n)) rc = fail(MXD_ERR_IO, "untgz: truncated archive");
+                left -= n;
+            }
         }
     }
     gzclose(gz);

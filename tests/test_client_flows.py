@@ -129,6 +129,17 @@ def test_directory_blobs_are_packed_pushed_and_pulled(any_engine, tmp_path):
     with pytest.raises(modelx_b200.MxdError):
         client.untgz(str(evil2), str(tmp_path / "y" / "z"), lib=any_engine._lib)
     assert not (tmp_path / "outside" / "pwned.txt").exists()
+    # a header that announces a multi-gigabyte extended-header body (or a huge device/fifo entry) must not be allocated
+    import gzip
+    evil3 = tmp_path / "evil3.tar.gz"
+    hdr = bytearray(512)
+    hdr[0:9] = b"PaxHeader"; hdr[100:107] = b"0000644"; hdr[124:135] = b"77777777777"; hdr[156:157] = b"x"
+    hdr[257:263] = b"ustar\0"; hdr[148:156] = b" " * 8
+    hdr[148:155] = b"%06o\0" % sum(hdr)
+    with gzip.open(evil3, "wb") as f:
+        f.write(bytes(hdr) + b"\0" * 1024)
+    with pytest.raises(modelx_b200.MxdError):
+        client.untgz(str(evil3), str(tmp_path / "w"), lib=any_engine._lib)
 
 
 def test_config1_push_then_pull_through_local_registry(any_engine, tmp_path):
