@@ -85,3 +85,21 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")):
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "liboracle" not in text and "oracle_lib" not in text and "orc_" not in text, os.path.join(dirpath, f)
+
+
+def test_go_shim_uses_only_declared_symbols():
+    """The cgo shim (integration/go, uncompiled here: no Go toolchain) may only call what include/modelx_digest.h declares
+    and the library exports."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "integration", "go", "pkg", "client", "digest_cuda.go")).read()
+    header = open(os.path.join(root, "include", "modelx_digest.h")).read()
+    used = set(re.findall(r"\bC\.((?:mxd|MXD)_[A-Za-z0-9_]+)", src))
+    assert used, "no C references found in the shim"
+    missing = sorted(s for s in used if not re.search(r"\b" + re.escape(s) + r"\b", header))
+    assert not missing, missing
+    import modelx_b200._native as N
+    lib = N.load()
+    for s in used:
+        if s.startswith("mxd_") and s not in ("mxd_ctx", "mxd_part", "mxd_span", "mxd_file_job", "mxd_stats", "mxd_hasher", "mxd_sink"):
+            assert hasattr(lib, s), s
