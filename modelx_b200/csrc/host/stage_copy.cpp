@@ -6,9 +6,9 @@
 // 16 threads, tmpfs file: pread 36.6 GB/s, memcpy out of an mmap 40 GB/s, AVX2 loads + NON-TEMPORAL stores out of an mmap
 // 56.8 GB/s (no RFO, no cache pollution; 4 threads: 18 / 19 / 27-31 GB/s).  In a bare process, that is.  Inside the library
 // the picture flips (profiles/r02_stage_copy_ab.txt, 24 GB file): pread 47.5 GB/s, mapped + streaming stores 32 GB/s,
-// mapped + memcpy 31 GB/s with 16 filler threads -- a process that holds a CUDA context pays far more per page fault
-// (the driver's MMU notifiers), and a fresh mapping of the file is all page faults; only when CPUs are scarce does the
-// cheaper copy win (2 CPUs: 11.4 vs 9.7 GB/s, 4 CPUs: 19.8 vs 18.8).  So the DEFAULT stays pread + memcpy, and
+// mapped + memcpy 31 GB/s with 16 filler threads.  Why is open: pre-filling the page tables of every piece with
+// madvise(MADV_POPULATE_READ) changes nothing (33.0 vs 32.4 GB/s, profiles/r02_stage_populate_ab.txt), so it is not the
+// per-page fault cost.  Only when CPUs are scarce does the cheaper copy win (2 CPUs: 11.4 vs 9.7 GB/s, 4 CPUs: 19.8 vs 18.8).  So the DEFAULT stays pread + memcpy, and
 // MXD_STAGE_MMAP=1 selects the mapped streaming-store copy for CPU-starved hosts.
 // A mapping can fault if the file is truncated while it is being hashed (pread would return a short read): the mapped copy
 // runs under a SIGBUS guard that turns the fault into "file shrank while hashing" instead of killing the host process;
