@@ -830,7 +830,9 @@ int fs_refresh_index(const std::string& basepath, const std::string& repo) {
         if (!manifest_from_json(text.c_str(), &keep[i], &err)) return fail(MXC_ERR_MANIFEST, "manifest invalid: " + names[i] + ": " + err);
         struct stat st; stat(join(mdir, names[i]).c_str(), &st);
         Descriptor desc; desc.name = names[i]; desc.modified = go_time_json(st.st_mtim); desc.annotations = keep[i].annotations;
-        desc.size = keep[i].config.size; for (auto& b : keep[i].blobs) desc.size += b.size;
+        // Go sums int64 sizes with wrap-around (store_fs.go:205-212); same bits here, without the signed-overflow UB
+        uint64_t total = (uint64_t)keep[i].config.size; for (auto& b : keep[i].blobs) total += (uint64_t)b.size;
+        desc.size = (int64_t)total;
         list.push_back(std::move(desc));
         if (!idx_ann && !keep[i].annotations.empty()) idx_ann = &keep[i].annotations;
     }
