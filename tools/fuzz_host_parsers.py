@@ -51,6 +51,18 @@ for i in range(iters):
     d = mutate("sha256:" + "ab" * 32)
     buf = (C.c_uint8 * 32)(); lib.mxd_digest_parse(d, buf)
     lib.mxc_blob_digest_path(mutate("library/m"), d, C.byref(out)); take()
+    if i % 5 == 0:                                    # the digest cache file and a stored manifest / index read back by pull
+        os.makedirs(os.path.join(base, ".modelx"), exist_ok=True)
+        cache = json.dumps({"a.bin": {"size": 1000, "mtime_ns": os.stat(os.path.join(base, "a.bin")).st_mtime_ns, "digest": "sha256:" + "3" * 64}})
+        open(os.path.join(base, ".modelx", "digests.json"), "wb").write(mutate(cache))
+        lib.mxc_push_digest(eng.handle, base.encode(), b"modelx.yaml", 2, C.byref(out)); take()
+        reg = os.path.join(work, "reg2"); mdir = os.path.join(reg, "library", "m", "manifests"); os.makedirs(mdir, exist_ok=True)
+        open(os.path.join(mdir, "v1"), "wb").write(m)
+        open(os.path.join(reg, "library", "m", "index.json"), "wb").write(mutate(good))
+        lib.mxc_fs_get_manifest(reg.encode(), b"library/m", b"v1", C.byref(out)); take()
+        lib.mxc_fs_get_index(reg.encode(), b"library/m", C.byref(out)); take()
+        lib.mxc_fs_get_index(reg.encode(), b"", C.byref(out)); take()
+        lib.mxc_pull_local(eng.handle, reg.encode(), b"library/m", b"v1", os.path.join(work, "into").encode(), C.byref(out)); take()
     if i % 10 == 0:                                   # archives: a valid tar.gz with a few entries, then byte damage inside the tar stream
         raw = io.BytesIO()
         with tarfile.open(fileobj=raw, mode="w") as tf:
