@@ -5,8 +5,8 @@
 //   CGO_ENABLED=1 go build -tags modelx_cuda ./cmd/modelx
 // The default build (CGO_ENABLED=0, Makefile:63) keeps using digest_purego.go.
 //
-// Routing rule (INTEGRATION.md section 3): one whole-file SHA-256 is one serial chain -- ~0.07-0.1 GB/s on a GPU
-// lane against ~1.4 GB/s on a SHA-NI core -- so the GPU is used only for WIDTH:
+// Routing rule (INTEGRATION.md section 3): one whole-file SHA-256 is one serial chain -- ~0.08 GB/s on the GPU
+// against ~1.4 GB/s on a SHA-NI core -- so the GPU is used only for WIDTH:
 //   - prefetchDigests hashes ALL blobs of a Push / Pull as one coalesced batch before the 3-goroutine fan-out, and
 //     only when mxd_batch_pays_off says the batch beats three CPU cores; pushFile / pullFile then find the digest
 //     already there (pushFile skips hashing when desc.Digest is set, push.go:125);
@@ -124,12 +124,19 @@ func prefetchDigests(ctx context.Context, paths []string) (context.Context, erro
 		return ctx, nil
 	}
 	n := len(present)
+	// The job array holds pointers, so everything it points to lives in C memory: cgo forbids passing Go memory that
+	// itself contains Go pointers (go 1.20, no runtime.Pinner yet).
 	jobs := make([]C.mxd_file_job, n)
-	out := make([]C.uint8_t, 32*n)
+	out := (*C.uint8_t)(C.calloc(C.size_t(n), 32))
+	if out == nil {
+		return ctx, errors.New("modelxdigest: out of memory")
+	}
+	defer C.free(unsafe.Pointer(out))
+	outAt := func(i int) *C.uint8_t { return (*C.uint8_t)(unsafe.Add(unsafe.Pointer(out), 32*i)) }
 	for i, p := range present {
 		jobs[i].path = C.CString(p)
 		defer C.free(unsafe.Pointer(jobs[i].path))
-		jobs[i].out = &out[32*i]
+		jobs[i].out = outAt(i)
 	}
 	if err := withOp(ctx, func(op *C.mxd_ctx) C.int {
 		rc := C.mxd_sha256_file_jobs(op, &jobs[0], C.uint64_t(n))
@@ -146,7 +153,7 @@ func prefetchDigests(ctx context.Context, paths []string) (context.Context, erro
 			continue
 		}
 		var s [72]C.char
-		C.mxd_digest_string(&out[32*i], &s[0])
+		C.mxd_digest_string(outAt(i), &s[0])
 		m[p] = digest.Digest(C.GoString(&s[0]))
 	}
 	return context.WithValue(ctx, digestCacheKey{}, m), nil
@@ -159,7 +166,7 @@ func digestFile(ctx context.Context, path string) (digest.Digest, error) {
 		return d, nil
 	}
 	if os.Getenv("MODELX_DIGEST_FORCE_GPU") == "" {
-		return digestFileGo(ctx, path) // a lone chain: the CPU is ~15x faster
+		return digestFileGo(ctx, path) // a lone chain: the CPU is ~18x faster
 	}
 	var out [32]C.uint8_t
 	var size C.uint64_t
