@@ -6,7 +6,6 @@ import ctypes as C, gzip, io, json, os, random, sys, tarfile, tempfile
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from tests import mock_build
 import modelx_b200
-from modelx_b200 import _native as N
 
 lib_path = mock_build.build(os.environ.get("MXD_MOCK_SANITIZE", ""))
 eng = modelx_b200.Engine(devices=[0], lib_path=lib_path)

@@ -1,7 +1,7 @@
 """Developer tool: randomized differential test of the HOST side of the tree digest (level assembly, ring cursor, file
 ranges, tee, sharded finish) against the oracle, through the CPU test double (optionally the ASan build).  Random
 (leaf, fanout, chunk = leaf * fanout^k), sizes around every boundary, tiny rings so that every slot wraps."""
-import hashlib, os, random, sys, tempfile
+import os, random, sys, tempfile
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from tests import mock_build
 from tests.oracle_lib import Oracle
